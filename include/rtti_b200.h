@@ -1,0 +1,133 @@
+/* rtti_b200 — C ABI of the B200-native region-diffusion hot path.
+ *
+ * The reference (songweige/rich-text-to-image) has no FFI: its hot path is Python calling ATen.
+ * Each entry point below replaces one (group of) reference call site(s); citations are
+ * file:line in the reference tree.  A Python/ctypes (or any other FFI) host binds exactly these
+ * symbols; see INTEGRATION.md for the reference-side stubs.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless marked "host".  The caller owns every buffer.
+ *   - No entry point allocates, synchronises, or touches a stream other than `stream`
+ *     (a cudaStream_t passed as void*); all are CUDA-graph capturable.
+ *   - fp16 = IEEE binary16 (`__half`), row-major, innermost dimension contiguous.
+ *   - Return value: RTTI_OK (0) or a negative RTTI_ERR_* code; nothing is launched on error.
+ *   - The caller selects the device (cudaSetDevice) before the call; sm_100 is required.
+ */
+#ifndef RTTI_B200_H
+#define RTTI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTTI_OK 0
+#define RTTI_ERR_ARG (-1)    /* null pointer / out-of-range argument */
+#define RTTI_ERR_SHAPE (-2)  /* unsupported shape (e.g. head_dim not a multiple of 8 or > 192) */
+#define RTTI_ERR_ALIGN (-3)  /* pointer not 16-byte aligned / stride not a multiple of 8 elements */
+#define RTTI_ERR_ARCH (-4)   /* device is not sm_100 */
+#define RTTI_ERR_CUDA (-5)   /* CUDA runtime / driver call failed (see cudaGetLastError) */
+
+/* Library version: major*10000 + minor*100 + patch. */
+int rtti_version(void);
+/* RTTI_OK when the current device can run these kernels (compute capability 10.x). */
+int rtti_arch_ok(void);
+
+/* Fused attention forward: O = softmax(scale * Q K^T) V per head, on tcgen05 tensor cores.
+ * Replaces Attention.get_attention_scores + torch.bmm + reshape_batch_dim_to_heads_and_average
+ * (models/attention_processor.py:359-407, 1157-1163, 166-171, 1181) and the hook passes that
+ * sit around them (models/region_diffusion_sdxl.py:959-1140).
+ *
+ *   q [batch, n_q, heads*head_dim], k/v [batch, n_k, heads*head_dim], o like q; fp16.
+ *   *_bs / *_rs: batch and row strides in ELEMENTS (multiples of 8); head h starts at column h*head_dim.
+ *   scale: softmax scale (head_dim^-0.5 in the reference, attention_processor.py:90).
+ *   qk_src (host, [batch] or NULL): batch entry whose Q and K produce the probabilities applied to
+ *       entry b's V — the self-attention injection of the region passes
+ *       (real_attn_probs, attention_processor.py:1160-1163; region_diffusion_sdxl.py:1023-1029).
+ *   word_pos [n_fs] int32, font_size [n_fs] fp32 (device), fs_batch_mask (bit b = apply to entry b):
+ *       font-size re-weighting  E[:, pos] *= |fs|;  P = E / sum(E);  P[:, pos] *= sign(fs)
+ *       (attention_processor.py:387-399; hooks region_diffusion_sdxl.py:1112-1140). Needs n_k <= 80.
+ *   pbar_accum [n_slots, n_q, n_k] fp32 (device), cap_slot (host, [batch], -1 = skip):
+ *       pbar_accum[cap_slot[b]] += mean over heads of P[b]  — the token-map capture of
+ *       region_diffusion_sdxl.py:965-992 without the D2H copy. Deterministic. Needs n_k <= 80.
+ *   lse [batch, heads, n_q] fp32 or NULL: log2-domain log-sum-exp of the scaled scores
+ *       (consumed by rtti_attn_probs_mean_accum).
+ */
+int rtti_attn_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads, int head_dim,
+                  int n_q, int n_k, long long q_bs, long long q_rs, long long k_bs, long long k_rs,
+                  long long v_bs, long long v_rs, long long o_bs, long long o_rs, float scale,
+                  const int* qk_src, const int* word_pos, const float* font_size, int n_fs,
+                  unsigned long long fs_batch_mask, float* pbar_accum, const int* cap_slot, float* lse,
+                  void* stream);
+
+/* Self-attention token-map capture: accum[n_q, n_k] += mean_h exp2(scale*log2e * Q_h K_h^T - lse_h)
+ * for ONE batch entry (the conditional row the reference keeps, region_diffusion_sdxl.py:989-992),
+ * recomputing QK^T on tensor cores instead of materialising P (attention_processor.py:1181).
+ *   q/k: [n_q|n_k, heads*head_dim] fp16 of that batch entry, row strides in elements;
+ *   lse: [heads, n_q] fp32 as written by rtti_attn_fwd for that entry.
+ */
+int rtti_attn_probs_mean_accum(const void* q, const void* k, const float* lse, float* accum, int heads,
+                               int head_dim, int n_q, int n_k, long long q_rs, long long k_rs, float scale,
+                               void* stream);
+
+/* GroupNorm (+ optional SiLU) over channels-last activations x[batch, hw, c] fp16.
+ * Replaces norm1/norm2 + nonlinearity of ResnetBlock2D (models/resnet.py:597-600, 624-629),
+ * Transformer2DModel.norm (models/transformer_2d.py:272) and conv_norm_out + conv_act
+ * (models/unet_2d_condition.py:975-977).  gamma/beta fp16 [c]; stats in fp32.
+ *   chan_bias: optional fp16 [batch, c] added to x before the statistics — the time-embedding add
+ *   `hidden_states + temb` that precedes norm2 (models/resnet.py:621-622), fused; NULL to skip.
+ *   workspace: fp32 [batch * ceil(hw/rows_per_block) * groups * 2] partial sums; query the element
+ *   count with rtti_groupnorm_workspace_elems.  Deterministic (no atomics).
+ */
+long long rtti_groupnorm_workspace_elems(int batch, int hw, int c, int groups);
+int rtti_groupnorm_silu_fwd(const void* x, const void* chan_bias, const void* gamma, const void* beta, void* y,
+                            float* workspace, int batch, int hw, int c, int groups, float eps, int apply_silu,
+                            void* stream);
+
+/* LayerNorm over the last dimension of x[rows, c] fp16 (models/attention.py:150,168,181). */
+int rtti_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int rows, int c, float eps,
+                       void* stream);
+
+/* GEGLU gate: y[rows, inner] = proj[rows, :inner] * gelu_erf(proj[rows, inner:])
+ * (models/attention.py:283-304). */
+int rtti_geglu_fwd(const void* proj, void* y, int rows, int inner, void* stream);
+
+/* Region blend + classifier-free guidance (+ optional Euler update), one launch.
+ * Replaces models/region_diffusion_sdxl.py:810-825 (and :845 when dt_sigma != 0):
+ *   eps_u = sum_i eps_uncond * m_i ; eps_t = sum_i eps_region[i] * m_i   (i over all n_regions masks,
+ *   eps_region[n_regions-1] is the base-prompt pass, masks[n_regions-1] the remainder mask)
+ *   eps = eps_u + guidance * (eps_t - eps_u)
+ *   latents_out = latents + dt_sigma * eps            (only when latents/latents_out non-NULL)
+ * eps_* fp16 [n], masks fp32 [n_regions, n], n = 4*h*w. eps_region rows may live in different
+ * buffers: `eps_region` is a host array of n_regions device pointers.
+ */
+int rtti_region_blend_cfg(const void* eps_uncond, const void* const* eps_region, const float* masks,
+                          int n_regions, long long n, float guidance, void* eps_out, const void* latents,
+                          void* latents_out, float dt_sigma, void* stream);
+
+/* Colour-guidance loss forward + analytic backward w.r.t. the VAE decoder output.
+ * Replaces models/region_diffusion_sdxl.py:857-865 (clamp, masked mean RGB, MSE*100, autograd of those).
+ *   decoded [3, hw] fp32 (VAE output before /2+0.5), masks [n_colors, hw] fp32 (channel 0 of
+ *   color_obj_atten), target_rgb [n_colors, 3] fp32.
+ *   loss_out [1] fp32; grad_decoded [3, hw] fp32 = d loss / d decoded.
+ *   workspace fp32 [rtti_color_loss_workspace_elems(n_colors, hw)].
+ */
+long long rtti_color_loss_workspace_elems(int n_colors, long long hw);
+int rtti_color_loss_fwd_bwd(const float* decoded, const float* masks, const float* target_rgb, int n_colors,
+                            long long hw, float* loss_out, float* grad_decoded, float* workspace, void* stream);
+
+/* latents_out = latents - grad * weight * atten_all   (models/region_diffusion_sdxl.py:866-867).
+ * latents fp16, grad fp32, atten_all fp32, all [n]. */
+int rtti_latent_guidance_update(const void* latents, const float* grad, const float* atten_all, float weight,
+                                void* latents_out, long long n, void* stream);
+
+/* out = latents_ref * m + latents * (1 - m)   (models/region_diffusion_sdxl.py:870-872). fp16, m fp32. */
+int rtti_bg_inject_blend(const void* latents, const void* latents_ref, const float* mask, void* out,
+                         long long n, void* stream);
+
+/* x0 = (x_t - eps * sqrt(1-alpha)) / sqrt(alpha)   (models/region_diffusion_sdxl.py:955-957). fp16. */
+int rtti_predict_x0(const void* x_t, const void* eps, float alpha, void* x0, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTTI_B200_H */

@@ -1,0 +1,213 @@
+"""Torch-tensor front end of the C ABI (include/rtti_b200.h).
+
+PyTorch is plumbing here: it owns the device memory and the stream; every op below hands raw
+pointers, sizes and the current CUDA stream to librtti_b200.so. No op has a PyTorch fallback.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+_F16 = torch.float16
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _req(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.RttiError(f"{name} must be a CUDA tensor (rtti_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.RttiError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _int_array(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def version():
+    return _lib.load().rtti_version()
+
+
+def arch_ok():
+    return _lib.load().rtti_arch_ok() == 0
+
+
+def _bsr(t):
+    """(batch stride, row stride) in elements of a [B, T, C] view whose last dim is contiguous."""
+    assert t.dim() == 3 and t.stride(2) == 1, "attention operands must be [B, T, heads*head_dim] with contiguous channels"
+    return t.stride(0), t.stride(1)
+
+
+def attention(q, k, v, heads, scale=None, qk_src=None, word_pos=None, font_size=None, fs_batch_mask=0,
+              pbar_accum=None, cap_slot=None, lse=None, out=None):
+    """Fused attention forward (rtti_attn_fwd). q [B,Nq,H*D], k/v [B,Nk,H*D] fp16 (strided views allowed)."""
+    lib = _lib.load()
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, _F16, n)
+    B, nq, C = q.shape
+    nk = k.shape[1]
+    D = C // heads
+    if out is None:
+        out = torch.empty((B, nq, C), dtype=_F16, device=q.device)
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    qb, qr = _bsr(q); kb, kr = _bsr(k); vb, vr = _bsr(v); ob, orr = _bsr(out)
+    n_fs = 0
+    if word_pos is not None and font_size is not None and fs_batch_mask:
+        _req(word_pos, torch.int32, "word_pos"); _req(font_size, torch.float32, "font_size")
+        n_fs = int(word_pos.numel())
+    rc = lib.rtti_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, heads, D, nq, nk, qb, qr, kb, kr, vb, vr, ob, orr,
+                           float(scale), _int_array(qk_src) if qk_src is not None else None,
+                           _ptr(word_pos) if n_fs else None, _ptr(font_size) if n_fs else None, n_fs,
+                           int(fs_batch_mask) if n_fs else 0,
+                           _ptr(pbar_accum) if pbar_accum is not None else None,
+                           _int_array(cap_slot) if cap_slot is not None else None,
+                           _ptr(lse) if lse is not None else None, _stream())
+    _lib.check(rc, "rtti_attn_fwd")
+    return out
+
+
+def attn_probs_mean_accum(q, k, lse, accum, heads, scale=None):
+    """accum[Nq,Nk] += mean_h softmax(scale q_h k_h^T) for one batch entry (rtti_attn_probs_mean_accum)."""
+    lib = _lib.load()
+    _req(q, _F16, "q"); _req(k, _F16, "k"); _req(lse, torch.float32, "lse"); _req(accum, torch.float32, "accum")
+    nq, C = q.shape
+    nk = k.shape[0]
+    D = C // heads
+    assert q.stride(1) == 1 and k.stride(1) == 1 and lse.is_contiguous() and accum.is_contiguous()
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    rc = lib.rtti_attn_probs_mean_accum(_ptr(q), _ptr(k), _ptr(lse), _ptr(accum), heads, D, nq, nk, q.stride(0),
+                                        k.stride(0), float(scale), _stream())
+    _lib.check(rc, "rtti_attn_probs_mean_accum")
+    return accum
+
+
+_gn_ws = {}
+
+
+def groupnorm_silu(x, gamma, beta, groups, eps, silu, chan_bias=None, out=None):
+    """GroupNorm(+temb bias)(+SiLU) on channels-last x[B, HW, C] fp16 (rtti_groupnorm_silu_fwd)."""
+    lib = _lib.load()
+    _req(x, _F16, "x"); _req(gamma, _F16, "gamma"); _req(beta, _F16, "beta")
+    assert x.dim() == 3 and x.is_contiguous()
+    B, HW, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    n = lib.rtti_groupnorm_workspace_elems(B, HW, C, groups)
+    key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 1 << 16), dtype=torch.float32, device=x.device)
+        _gn_ws[key] = ws
+    if chan_bias is not None:
+        _req(chan_bias, _F16, "chan_bias")
+        assert chan_bias.shape == (B, C) and chan_bias.is_contiguous()
+    rc = lib.rtti_groupnorm_silu_fwd(_ptr(x), _ptr(chan_bias), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(ws), B, HW, C,
+                                     groups, float(eps), 1 if silu else 0, _stream())
+    _lib.check(rc, "rtti_groupnorm_silu_fwd")
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out=None):
+    lib = _lib.load()
+    _req(x, _F16, "x"); _req(gamma, _F16, "gamma"); _req(beta, _F16, "beta")
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(lib.rtti_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, C, float(eps), _stream()),
+               "rtti_layernorm_fwd")
+    return out
+
+
+def geglu(proj, out=None):
+    lib = _lib.load()
+    _req(proj, _F16, "proj")
+    assert proj.is_contiguous()
+    inner = proj.shape[-1] // 2
+    rows = proj.numel() // (2 * inner)
+    if out is None:
+        out = torch.empty(proj.shape[:-1] + (inner,), dtype=_F16, device=proj.device)
+    _lib.check(lib.rtti_geglu_fwd(_ptr(proj), _ptr(out), rows, inner, _stream()), "rtti_geglu_fwd")
+    return out
+
+
+def region_blend_cfg(eps_uncond, eps_regions, masks, guidance, latents=None, dt_sigma=0.0):
+    """eps = eps_u + g (eps_t - eps_u) with the masked region sums; optionally latents + dt_sigma*eps.
+    eps_regions: list of fp16 tensors (region passes in mask order, base-prompt pass last); masks fp32 [N, n]."""
+    lib = _lib.load()
+    _req(eps_uncond, _F16, "eps_uncond"); _req(masks, torch.float32, "masks")
+    n = eps_uncond.numel()
+    N = len(eps_regions)
+    assert masks.is_contiguous() and masks.numel() == N * n
+    for e in eps_regions:
+        _req(e, _F16, "eps_region"); assert e.is_contiguous() and e.numel() == n
+    ptrs = (ctypes.c_void_p * N)(*[e.data_ptr() for e in eps_regions])
+    eps_out = torch.empty_like(eps_uncond)
+    lat_out = torch.empty_like(latents) if latents is not None else None
+    rc = lib.rtti_region_blend_cfg(_ptr(eps_uncond), ptrs, _ptr(masks), N, n, float(guidance), _ptr(eps_out),
+                                   _ptr(latents), _ptr(lat_out), float(dt_sigma), _stream())
+    _lib.check(rc, "rtti_region_blend_cfg")
+    return (eps_out, lat_out) if latents is not None else eps_out
+
+
+_cl_ws = {}
+
+
+def color_loss_fwd_bwd(decoded, masks, target_rgb):
+    """decoded [3,H,W] fp32 (pre-clamp VAE output), masks [R,H,W] fp32, target_rgb [R,3] fp32 -> (loss[1], grad[3,H,W])."""
+    lib = _lib.load()
+    for t, nme in ((decoded, "decoded"), (masks, "masks"), (target_rgb, "target_rgb")):
+        _req(t, torch.float32, nme); assert t.is_contiguous()
+    R = masks.shape[0]
+    hw = decoded.numel() // 3
+    n = lib.rtti_color_loss_workspace_elems(R, hw)
+    ws = _cl_ws.get(decoded.device.index)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(n, dtype=torch.float32, device=decoded.device)
+        _cl_ws[decoded.device.index] = ws
+    loss = torch.empty(1, dtype=torch.float32, device=decoded.device)
+    grad = torch.empty_like(decoded)
+    rc = lib.rtti_color_loss_fwd_bwd(_ptr(decoded), _ptr(masks), _ptr(target_rgb), R, hw, _ptr(loss), _ptr(grad),
+                                     _ptr(ws), _stream())
+    _lib.check(rc, "rtti_color_loss_fwd_bwd")
+    return loss, grad
+
+
+def latent_guidance_update(latents, grad, atten_all, weight):
+    lib = _lib.load()
+    _req(latents, _F16, "latents"); _req(grad, torch.float32, "grad"); _req(atten_all, torch.float32, "atten_all")
+    out = torch.empty_like(latents)
+    rc = lib.rtti_latent_guidance_update(_ptr(latents), _ptr(grad.contiguous()), _ptr(atten_all.contiguous()),
+                                         float(weight), _ptr(out), latents.numel(), _stream())
+    _lib.check(rc, "rtti_latent_guidance_update")
+    return out
+
+
+def bg_inject_blend(latents, latents_ref, mask):
+    lib = _lib.load()
+    _req(latents, _F16, "latents"); _req(latents_ref, _F16, "latents_ref"); _req(mask, torch.float32, "mask")
+    out = torch.empty_like(latents)
+    rc = lib.rtti_bg_inject_blend(_ptr(latents), _ptr(latents_ref), _ptr(mask.contiguous()), _ptr(out),
+                                  latents.numel(), _stream())
+    _lib.check(rc, "rtti_bg_inject_blend")
+    return out
+
+
+def predict_x0(x_t, eps, alpha):
+    lib = _lib.load()
+    _req(x_t, _F16, "x_t"); _req(eps, _F16, "eps")
+    out = torch.empty_like(x_t)
+    _lib.check(lib.rtti_predict_x0(_ptr(x_t), _ptr(eps), float(alpha), _ptr(out), x_t.numel(), _stream()),
+               "rtti_predict_x0")
+    return out
