@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     if force or _newer(objs, LIB_PATH):
-        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-cudart", "static"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
