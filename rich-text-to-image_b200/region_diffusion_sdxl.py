@@ -1,0 +1,272 @@
+"""RegionDiffusionXL — B200-native drop-in for models/region_diffusion_sdxl.py of the reference.
+
+Same public surface (`sample(...)`, `register_tokenmap_hooks / remove_tokenmap_hooks`, `.masks`,
+`.selfattn_maps / .crossattn_maps / .n_maps`, `.unet .vae .scheduler .tokenizer`) and the same per-step
+semantics (models/region_diffusion_sdxl.py:772-914), re-organised for the hardware:
+
+  * the 2 + 2*inject + (N-1) UNet passes of a step (uncond, base+font-size, reference uncond, reference
+    base, N-1 regions; :787-821) run as ONE batched UNet call — they share the timestep and, up to the
+    reference latent, the input; the hook choreography becomes a RegionControl;
+  * region blend + CFG + Euler update is one kernel (rtti_region_blend_cfg); colour-guidance loss fwd/bwd,
+    guidance update, x0 prediction and background injection are kernels too;
+  * with torch.distributed initialised the passes are sharded over the ranks (region_parallel.py) and the
+    per-pass noise predictions are all-gathered before the (replicated, deterministic) blend.
+"""
+import math
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import ops, region_parallel
+from .attention_utils import CrossAttentionLayers_XL
+from .schedulers import EulerDiscreteScheduler
+from .unet import CrossKVCache, RegionControl, TokenMapAccumulator, UNet2DConditionModel, UNetConfig
+from .vae import AutoencoderKLDecoder, VAEConfig
+
+
+class StableDiffusionXLPipelineOutput(dict):
+    def __init__(self, images):
+        super().__init__(images=images)
+        self.images = images
+
+
+class RegionDiffusionXL:
+    def __init__(self, load_path: str = "stabilityai/stable-diffusion-xl-base-1.0", device: str = "cuda",
+                 force_zeros_for_empty_prompt: bool = True, unet=None, vae=None, scheduler=None,
+                 text_encoders=None):
+        """Either pass pre-built components (tests / synthetic benchmarks) or a local diffusers-format
+        directory as `load_path` (models/region_diffusion_sdxl.py:87-137 downloads from the hub; there is
+        no network here, so only local paths are supported)."""
+        self.device = torch.device(device)
+        self.device_type = device
+        if unet is None:
+            from .loading import load_sdxl_components
+            unet, vae, scheduler, text_encoders = load_sdxl_components(load_path, self.device)
+        self.unet = unet
+        self.vae = vae
+        self.scheduler = scheduler or EulerDiscreteScheduler()
+        self.text_encoders = text_encoders
+        self.tokenizer = getattr(text_encoders, "tokenizer", None)
+        self.tokenizer_2 = getattr(text_encoders, "tokenizer_2", None)
+        self.force_zeros_for_empty_prompt = force_zeros_for_empty_prompt
+        self.vae_scale_factor = 8
+        self.default_sample_size = unet.config.sample_size
+        self.masks = []
+        self.attention_maps = None
+        self.selfattn_maps = None
+        self.crossattn_maps = None
+        self.n_maps = None
+        self._capture = None
+        self.capture_all_resolutions = False
+        self.last_step_stats = {}
+
+    @classmethod
+    def from_synthetic(cls, unet_cfg: Optional[UNetConfig] = None, vae_cfg: Optional[VAEConfig] = None, seed=0,
+                       device="cuda", with_vae=True):
+        """Random-weight model of the right architecture (benchmarks / tests; no checkpoints available)."""
+        unet = UNet2DConditionModel(unet_cfg or UNetConfig.sdxl())
+        unet.finalize(device).init_synthetic(seed)
+        vae = None
+        if with_vae:
+            vae = AutoencoderKLDecoder(vae_cfg or VAEConfig.sdxl()).init_synthetic(seed + 1).finalize(device)
+        return cls(device=device, unet=unet, vae=vae, scheduler=EulerDiscreteScheduler())
+
+    # ------------------------------------------------------------------ token-map capture API
+    def register_tokenmap_hooks(self):
+        """models/region_diffusion_sdxl.py:959-1009 — here: arm the on-device accumulators."""
+        res = None if self.capture_all_resolutions else (32,)
+        self._capture = TokenMapAccumulator(CrossAttentionLayers_XL, self_layers=None, start_after=10,
+                                            sd_overwrite_bug=False, self_resolutions=res)
+        self.selfattn_maps = self._capture.selfattn_maps
+        self.crossattn_maps = self._capture.crossattn_maps
+        self.n_maps = self._capture.n_maps
+
+    def remove_tokenmap_hooks(self):
+        self._capture = None
+        self.selfattn_maps = None
+        self.crossattn_maps = None
+        self.n_maps = None
+
+    # ------------------------------------------------------------------ helpers
+    def encode_prompt(self, prompt, negative_prompt):
+        if self.text_encoders is None:
+            raise RuntimeError("no text encoders loaded: pass prompt_embeds / pooled_prompt_embeds explicitly")
+        return self.text_encoders.encode(prompt, negative_prompt, self.device)
+
+    def prepare_latents(self, height, width, generator=None, latents=None):
+        shape = (1, self.unet.config.in_channels, height // self.vae_scale_factor, width // self.vae_scale_factor)
+        if latents is None:
+            latents = torch.randn(shape, generator=generator, device=self.device, dtype=torch.float16)
+        else:
+            latents = latents.to(self.device, torch.float16)
+        return latents * self.scheduler.init_noise_sigma
+
+    def predict_x0(self, x_t, eps_t, t):
+        """models/region_diffusion_sdxl.py:955-957 (alphas_cumprod[int(t)] with the post-step latents)."""
+        alpha = float(self.scheduler.alphas_cumprod[int(float(t))])
+        return ops.predict_x0(x_t.contiguous(), eps_t.contiguous(), alpha), alpha
+
+    def _color_guidance(self, latents, noise_pred, t, tfd):
+        """models/region_diffusion_sdxl.py:849-867 with the clamp / masked mean / MSE forward+backward in
+        rtti_color_loss_fwd_bwd and the VAE (third-party) in PyTorch autograd with frozen weights."""
+        x0, alpha = self.predict_x0(latents, noise_pred, t)
+        sf = self.vae.config.scaling_factor
+        z = (x0.float() / sf).requires_grad_(True)
+        with torch.enable_grad():
+            dec = self.vae.decode_tensor(z)
+        masks = torch.stack([m[0, 0].to(self.device, torch.float32) for m in tfd["color_obj_atten"]]).contiguous()
+        tgt = torch.stack([r.reshape(3).to(self.device, torch.float32) for r in tfd["target_RGB"]]).contiguous()
+        dec_c = dec.detach()[0].contiguous()
+        loss, g = ops.color_loss_fwd_bwd(dec_c, masks, tgt)
+        dec.backward(g[None].contiguous(memory_format=torch.channels_last) if dec.is_contiguous(memory_format=torch.channels_last) else g[None])
+        grad_lat = z.grad / (sf * math.sqrt(alpha))
+        atten_all = tfd["color_obj_atten_all"].to(self.device, torch.float32).expand_as(grad_lat).contiguous()
+        self.last_step_stats["color_loss"] = loss
+        return ops.latent_guidance_update(latents.contiguous(), grad_lat.contiguous(), atten_all,
+                                          float(tfd["color_guidance_weight"]))
+
+    # ------------------------------------------------------------------ sampling
+    @torch.no_grad()
+    def sample(self, prompt=None, height: Optional[int] = None, width: Optional[int] = None,
+               num_inference_steps: int = 50, guidance_scale: float = 5.0, negative_prompt=None,
+               num_images_per_prompt: int = 1, eta: float = 0.0, generator=None, latents=None, prompt_embeds=None,
+               negative_prompt_embeds=None, pooled_prompt_embeds=None, negative_pooled_prompt_embeds=None,
+               output_type: Optional[str] = "pil", return_dict: bool = True, callback=None, callback_steps: int = 1,
+               cross_attention_kwargs=None, guidance_rescale: float = 0.0, original_size=None,
+               crops_coords_top_left=(0, 0), target_size=None, use_guidance: bool = False,
+               inject_selfattn: float = 0.0, inject_background: float = 0.0, text_format_dict: Optional[dict] = None,
+               run_rich_text: bool = False):
+        """Signature of models/region_diffusion_sdxl.py:556-587. `prompt` is the list of region prompts with the
+        base prompt last (sample.py:107); embeddings may be passed instead of text."""
+        height = height or self.default_sample_size * self.vae_scale_factor
+        width = width or self.default_sample_size * self.vae_scale_factor
+        original_size = original_size or (height, width)
+        target_size = target_size or (height, width)
+        if guidance_rescale > 0.0 and run_rich_text:
+            raise NotImplementedError  # as the reference, :826-829
+        if prompt_embeds is None:
+            prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds = \
+                self.encode_prompt(prompt, negative_prompt)
+        dev = self.device
+        # [uncond, prompts...] like :760-763
+        ctx = torch.cat([negative_prompt_embeds, prompt_embeds], 0).to(dev, torch.float16)
+        pooled = torch.cat([negative_pooled_prompt_embeds, pooled_prompt_embeds], 0).to(dev, torch.float16)
+        time_ids = torch.tensor([list(original_size) + list(crops_coords_top_left) + list(target_size)],
+                                dtype=torch.float32, device=dev)
+        self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        timesteps = self.scheduler.timesteps
+        latents = self.prepare_latents(height, width, generator, latents)
+
+        if run_rich_text:
+            latents = self._rich_text_loop(ctx, pooled, time_ids, latents, timesteps, guidance_scale, use_guidance,
+                                           inject_selfattn, inject_background, text_format_dict or {}, callback,
+                                           callback_steps)
+        else:
+            latents = self._plain_loop(ctx, pooled, time_ids, latents, timesteps, guidance_scale, callback, callback_steps)
+
+        if output_type == "latent":
+            return StableDiffusionXLPipelineOutput(images=latents)
+        image = self.vae.decode_tensor(latents.float() / self.vae.config.scaling_factor)
+        image = (image / 2 + 0.5).clamp(0, 1)
+        if output_type == "pt":
+            return StableDiffusionXLPipelineOutput(images=image)
+        arr = (image.permute(0, 2, 3, 1).float().cpu().numpy() * 255).round().astype("uint8")
+        if output_type == "np":
+            return StableDiffusionXLPipelineOutput(images=arr)
+        from PIL import Image
+        return StableDiffusionXLPipelineOutput(images=[Image.fromarray(a) for a in arr])
+
+    def _plain_loop(self, ctx, pooled, time_ids, latents, timesteps, guidance_scale, callback, callback_steps):
+        """:879-914 — CFG batch [uncond, cond]; with capture armed the attention kernels accumulate the maps."""
+        ctx2 = torch.cat([ctx[:1], ctx[-1:]])
+        pooled2 = torch.cat([pooled[:1], pooled[-1:]])
+        kv = CrossKVCache()
+        ones = None
+        for i, t in enumerate(timesteps):
+            sigma = self.scheduler.sigma(t)
+            x = (latents / math.sqrt(sigma * sigma + 1.0)).expand(2, -1, -1, -1)
+            ctrl = RegionControl(capture=self._capture, capture_row=1, kv_cache=kv)
+            eps = self.unet(x, t, ctx2, {"text_embeds": pooled2, "time_ids": time_ids}, ctrl)["sample"]
+            n = eps[0].numel()
+            if ones is None:
+                ones = torch.ones(1, n, dtype=torch.float32, device=eps.device)
+            _, latents = ops.region_blend_cfg(eps[0:1].contiguous(), [eps[1:2].contiguous()], ones, guidance_scale,
+                                              latents=latents.contiguous(), dt_sigma=self.scheduler.dt(t))
+            if callback is not None and i % callback_steps == 0:
+                callback(i, t, latents)
+        return latents
+
+    def build_pass_batch(self, n_regions, inject):
+        """Order of the batched passes of one step and the context row each one uses.
+        rows index [uncond, region_1..region_{N-1}, base] (ctx); `x_ref` marks the reference-latent passes."""
+        last = n_regions  # ctx row of the base prompt
+        passes = [dict(kind="A", ctx=0, ref=False), dict(kind="B", ctx=last, ref=False)]
+        if inject:
+            passes += [dict(kind="C", ctx=0, ref=True), dict(kind="D", ctx=last, ref=True)]
+        for j in range(n_regions - 1):
+            passes.append(dict(kind="E", ctx=j + 1, ref=False, region=j))
+        return passes
+
+    def _rich_text_loop(self, ctx, pooled, time_ids, latents, timesteps, guidance_scale, use_guidance,
+                        inject_selfattn, inject_background, tfd, callback, callback_steps):
+        """:772-878."""
+        dev = self.device
+        N = len(self.masks)
+        assert ctx.shape[0] == N + 1, "prompts must be [region_1..region_{N-1}, base] matching self.masks"
+        inject = inject_selfattn > 0 or inject_background > 0
+        n_lat = latents[0].numel()
+        masks = torch.stack([m.to(dev, torch.float32).reshape(-1) for m in self.masks]).contiguous()  # [N, n] (:776)
+        ones = torch.ones(1, n_lat, dtype=torch.float32, device=dev)
+        latents_ref = latents.clone() if inject else None
+        passes = self.build_pass_batch(N, inject)
+        plan = region_parallel.RegionParallelPlan(passes, inject)
+        word_pos = tfd.get("word_pos")
+        font_size = tfd.get("font_size")
+        if word_pos is not None and font_size is not None:
+            word_pos = word_pos.to(dev, torch.int32).contiguous()
+            font_size = font_size.to(dev, torch.float32).contiguous()
+        else:
+            word_pos = font_size = None
+        kv_caches = {}
+        n_t = len(timesteps)
+        for i, t in enumerate(timesteps):
+            feat_inject_step = bool(float(t) > (1 - inject_selfattn) * 1000)            # :782
+            background_inject_step = i < inject_background * n_t                         # :783
+            sigma = self.scheduler.sigma(t)
+            scale = 1.0 / math.sqrt(sigma * sigma + 1.0)                                 # :784
+            local = plan.local_passes(feat_inject_step)
+            key = tuple(local)
+            if key not in kv_caches:
+                kv_caches[key] = CrossKVCache()
+            rows = [passes[p]["ctx"] for p in local]
+            x = torch.cat([(latents_ref if passes[p]["ref"] else latents) for p in local]) * scale
+            ctrl = RegionControl(kv_cache=kv_caches[key])
+            if feat_inject_step and inject:
+                src = plan.injection_sources(local)                                      # :1018-1061
+                ctrl.qk_src = src
+                ctrl.feature_src = src
+            if word_pos is not None:
+                b_idx = [k for k, p in enumerate(local) if passes[p]["kind"] == "B"]     # :792-797
+                ctrl.word_pos, ctrl.font_size = word_pos, font_size
+                ctrl.fs_batch_mask = sum(1 << k for k in b_idx)
+            eps_local = self.unet(x, t, ctx[rows], {"text_embeds": pooled[rows], "time_ids": time_ids}, ctrl)["sample"]
+            eps = plan.gather(eps_local, local, feat_inject_step)  # [n_passes, 4, h, w]; identity on one GPU
+            kind = {p["kind"] + str(p.get("region", "")): k for k, p in enumerate(passes)}
+            eps_u = eps[kind["A"]:kind["A"] + 1].contiguous()
+            regions = [eps[kind[f"E{j}"]:kind[f"E{j}"] + 1].contiguous() for j in range(N - 1)]
+            regions.append(eps[kind["B"]:kind["B"] + 1].contiguous())
+            dt = self.scheduler.dt(t)
+            noise_pred, latents = ops.region_blend_cfg(eps_u, regions, masks, guidance_scale,
+                                                       latents=latents.contiguous(), dt_sigma=dt)   # :810-825, :845
+            if inject and (inject_selfattn > 0 or background_inject_step):                           # :830-841
+                _, latents_ref = ops.region_blend_cfg(eps[kind["C"]:kind["C"] + 1].contiguous(),
+                                                      [eps[kind["D"]:kind["D"] + 1].contiguous()], ones,
+                                                      guidance_scale, latents=latents_ref.contiguous(), dt_sigma=dt)
+            if use_guidance and float(t) < tfd["guidance_start_step"]:                                # :849
+                latents = self._color_guidance(latents, noise_pred, t, tfd)
+            if i == int(inject_background * n_t) and inject_background > 0:                           # :870-872
+                latents = ops.bg_inject_blend(latents.contiguous(), latents_ref.contiguous(), masks[-1].contiguous())
+            if callback is not None and i % callback_steps == 0:
+                callback(i, t, latents)
+        return latents
