@@ -12,6 +12,16 @@ from . import _lib
 
 _F16 = torch.float16
 
+# number of kernels of librtti_b200.so launched since import (bench.py reports the count of a timed region)
+LAUNCHES = 0
+# when a list: attention() appends (start_event, end_event, kind, flops, algorithmic_bytes) per launch
+PROFILE = None
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -64,6 +74,10 @@ def attention(q, k, v, heads, scale=None, qk_src=None, word_pos=None, font_size=
     if word_pos is not None and font_size is not None and fs_batch_mask:
         _req(word_pos, torch.int32, "word_pos"); _req(font_size, torch.float32, "font_size")
         n_fs = int(word_pos.numel())
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = lib.rtti_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, heads, D, nq, nk, qb, qr, kb, kr, vb, vr, ob, orr,
                            float(scale), _int_array(qk_src) if qk_src is not None else None,
                            _ptr(word_pos) if n_fs else None, _ptr(font_size) if n_fs else None, n_fs,
@@ -72,6 +86,12 @@ def attention(q, k, v, heads, scale=None, qk_src=None, word_pos=None, font_size=
                            _int_array(cap_slot) if cap_slot is not None else None,
                            _ptr(lse) if lse is not None else None, _stream())
     _lib.check(rc, "rtti_attn_fwd")
+    _count(1)
+    if prof is not None:
+        ev1.record()
+        flops = 4.0 * B * heads * nq * nk * D
+        nbytes = 2.0 * (2 * B * nq * C + 2 * B * nk * C)
+        prof.append((ev0, ev1, "self" if nk > 80 else "cross", flops, nbytes, (B, heads, D, nq, nk)))
     return out
 
 
@@ -88,6 +108,7 @@ def attn_probs_mean_accum(q, k, lse, accum, heads, scale=None):
     rc = lib.rtti_attn_probs_mean_accum(_ptr(q), _ptr(k), _ptr(lse), _ptr(accum), heads, D, nq, nk, q.stride(0),
                                         k.stride(0), float(scale), _stream())
     _lib.check(rc, "rtti_attn_probs_mean_accum")
+    _count(1)
     return accum
 
 
@@ -114,6 +135,7 @@ def groupnorm_silu(x, gamma, beta, groups, eps, silu, chan_bias=None, out=None):
     rc = lib.rtti_groupnorm_silu_fwd(_ptr(x), _ptr(chan_bias), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(ws), B, HW, C,
                                      groups, float(eps), 1 if silu else 0, _stream())
     _lib.check(rc, "rtti_groupnorm_silu_fwd")
+    _count(2)
     return out
 
 
@@ -127,6 +149,7 @@ def layernorm(x, gamma, beta, eps, out=None):
         out = torch.empty_like(x)
     _lib.check(lib.rtti_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, C, float(eps), _stream()),
                "rtti_layernorm_fwd")
+    _count(1)
     return out
 
 
@@ -139,6 +162,7 @@ def geglu(proj, out=None):
     if out is None:
         out = torch.empty(proj.shape[:-1] + (inner,), dtype=_F16, device=proj.device)
     _lib.check(lib.rtti_geglu_fwd(_ptr(proj), _ptr(out), rows, inner, _stream()), "rtti_geglu_fwd")
+    _count(1)
     return out
 
 
@@ -158,6 +182,7 @@ def region_blend_cfg(eps_uncond, eps_regions, masks, guidance, latents=None, dt_
     rc = lib.rtti_region_blend_cfg(_ptr(eps_uncond), ptrs, _ptr(masks), N, n, float(guidance), _ptr(eps_out),
                                    _ptr(latents), _ptr(lat_out), float(dt_sigma), _stream())
     _lib.check(rc, "rtti_region_blend_cfg")
+    _count(1)
     return (eps_out, lat_out) if latents is not None else eps_out
 
 
@@ -181,6 +206,7 @@ def color_loss_fwd_bwd(decoded, masks, target_rgb):
     rc = lib.rtti_color_loss_fwd_bwd(_ptr(decoded), _ptr(masks), _ptr(target_rgb), R, hw, _ptr(loss), _ptr(grad),
                                      _ptr(ws), _stream())
     _lib.check(rc, "rtti_color_loss_fwd_bwd")
+    _count(3)
     return loss, grad
 
 
@@ -191,6 +217,7 @@ def latent_guidance_update(latents, grad, atten_all, weight):
     rc = lib.rtti_latent_guidance_update(_ptr(latents), _ptr(grad.contiguous()), _ptr(atten_all.contiguous()),
                                          float(weight), _ptr(out), latents.numel(), _stream())
     _lib.check(rc, "rtti_latent_guidance_update")
+    _count(1)
     return out
 
 
@@ -201,6 +228,7 @@ def bg_inject_blend(latents, latents_ref, mask):
     rc = lib.rtti_bg_inject_blend(_ptr(latents), _ptr(latents_ref), _ptr(mask.contiguous()), _ptr(out),
                                   latents.numel(), _stream())
     _lib.check(rc, "rtti_bg_inject_blend")
+    _count(1)
     return out
 
 
@@ -210,4 +238,5 @@ def predict_x0(x_t, eps, alpha):
     out = torch.empty_like(x_t)
     _lib.check(lib.rtti_predict_x0(_ptr(x_t), _ptr(eps), float(alpha), _ptr(out), x_t.numel(), _stream()),
                "rtti_predict_x0")
+    _count(1)
     return out

@@ -42,7 +42,8 @@ class RegionDiffusion:
     @classmethod
     def from_synthetic(cls, unet_cfg: Optional[UNetConfig] = None, vae_cfg: Optional[VAEConfig] = None, seed=0,
                        device="cuda", with_vae=True):
-        unet = UNet2DConditionModel(unet_cfg or UNetConfig.sd15())
+        with torch.device(device):
+            unet = UNet2DConditionModel(unet_cfg or UNetConfig.sd15())
         unet.finalize(device).init_synthetic(seed)
         vae = AutoencoderKLDecoder(vae_cfg or VAEConfig.sd15()).init_synthetic(seed + 1).finalize(device) if with_vae else None
         return cls(device=device, unet=unet, vae=vae)

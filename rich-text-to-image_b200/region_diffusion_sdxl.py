@@ -65,7 +65,8 @@ class RegionDiffusionXL:
     def from_synthetic(cls, unet_cfg: Optional[UNetConfig] = None, vae_cfg: Optional[VAEConfig] = None, seed=0,
                        device="cuda", with_vae=True):
         """Random-weight model of the right architecture (benchmarks / tests; no checkpoints available)."""
-        unet = UNet2DConditionModel(unet_cfg or UNetConfig.sdxl())
+        with torch.device(device):  # build directly on the GPU: CPU default-init of 2.6 B parameters is slow
+            unet = UNet2DConditionModel(unet_cfg or UNetConfig.sdxl())
         unet.finalize(device).init_synthetic(seed)
         vae = None
         if with_vae:
@@ -208,65 +209,80 @@ class RegionDiffusionXL:
             passes.append(dict(kind="E", ctx=j + 1, ref=False, region=j))
         return passes
 
-    def _rich_text_loop(self, ctx, pooled, time_ids, latents, timesteps, guidance_scale, use_guidance,
-                        inject_selfattn, inject_background, tfd, callback, callback_steps):
-        """:772-878."""
+    def prepare_rich_text(self, ctx, pooled, time_ids, latents, timesteps, guidance_scale, use_guidance,
+                          inject_selfattn, inject_background, tfd):
+        """Everything of :772-778 that is constant over the steps, as a state object for rich_text_step()."""
         dev = self.device
         N = len(self.masks)
         assert ctx.shape[0] == N + 1, "prompts must be [region_1..region_{N-1}, base] matching self.masks"
         inject = inject_selfattn > 0 or inject_background > 0
-        n_lat = latents[0].numel()
-        masks = torch.stack([m.to(dev, torch.float32).reshape(-1) for m in self.masks]).contiguous()  # [N, n] (:776)
-        ones = torch.ones(1, n_lat, dtype=torch.float32, device=dev)
-        latents_ref = latents.clone() if inject else None
-        passes = self.build_pass_batch(N, inject)
-        plan = region_parallel.RegionParallelPlan(passes, inject)
-        word_pos = tfd.get("word_pos")
-        font_size = tfd.get("font_size")
+        st = type("RichTextState", (), {})()
+        st.ctx, st.pooled, st.time_ids = ctx, pooled, time_ids
+        st.latents = latents
+        st.latents_ref = latents.clone() if inject else None
+        st.timesteps, st.n_t = timesteps, len(timesteps)
+        st.guidance_scale, st.use_guidance = guidance_scale, use_guidance
+        st.inject, st.inject_selfattn, st.inject_background = inject, inject_selfattn, inject_background
+        st.tfd = tfd
+        st.N = N
+        st.masks = torch.stack([m.to(dev, torch.float32).reshape(-1) for m in self.masks]).contiguous()  # [N, n] (:776)
+        st.ones = torch.ones(1, latents[0].numel(), dtype=torch.float32, device=dev)
+        st.passes = self.build_pass_batch(N, inject)
+        st.kind = {p["kind"] + str(p.get("region", "")): k for k, p in enumerate(st.passes)}
+        st.plan = region_parallel.RegionParallelPlan(st.passes, inject)
+        word_pos, font_size = tfd.get("word_pos"), tfd.get("font_size")
         if word_pos is not None and font_size is not None:
-            word_pos = word_pos.to(dev, torch.int32).contiguous()
-            font_size = font_size.to(dev, torch.float32).contiguous()
+            st.word_pos = word_pos.to(dev, torch.int32).contiguous()
+            st.font_size = font_size.to(dev, torch.float32).contiguous()
         else:
-            word_pos = font_size = None
-        kv_caches = {}
-        n_t = len(timesteps)
+            st.word_pos = st.font_size = None
+        st.kv_caches = {}
+        st.noise_pred = None
+        return st
+
+    def rich_text_step(self, st, i):
+        """One iteration of the region loop, models/region_diffusion_sdxl.py:779-878."""
+        t = st.timesteps[i]
+        passes, kind, plan, N = st.passes, st.kind, st.plan, st.N
+        feat_inject_step = bool(float(t) > (1 - st.inject_selfattn) * 1000)            # :782
+        background_inject_step = i < st.inject_background * st.n_t                      # :783
+        sigma = self.scheduler.sigma(t)
+        scale = 1.0 / math.sqrt(sigma * sigma + 1.0)                                    # :784
+        local = plan.local_passes(feat_inject_step)
+        kvc = st.kv_caches.setdefault(tuple(local), CrossKVCache())
+        rows = [passes[p]["ctx"] for p in local]
+        x = torch.cat([(st.latents_ref if passes[p]["ref"] else st.latents) for p in local]) * scale
+        ctrl = RegionControl(kv_cache=kvc)
+        if feat_inject_step and st.inject:
+            src = plan.injection_sources(local)                                         # :1018-1061
+            ctrl.qk_src = src
+            ctrl.feature_src = src
+        if st.word_pos is not None:
+            ctrl.word_pos, ctrl.font_size = st.word_pos, st.font_size                   # :792-797
+            ctrl.fs_batch_mask = sum(1 << k for k, p in enumerate(local) if passes[p]["kind"] == "B")
+        eps_local = self.unet(x, t, st.ctx[rows], {"text_embeds": st.pooled[rows], "time_ids": st.time_ids}, ctrl)["sample"]
+        eps = plan.gather(eps_local, local, feat_inject_step)   # [n_passes, 4, h, w]; identity on one GPU
+        one = lambda name: eps[kind[name]:kind[name] + 1].contiguous()
+        regions = [one(f"E{j}") for j in range(N - 1)] + [one("B")]
+        dt = self.scheduler.dt(t)
+        st.noise_pred, st.latents = ops.region_blend_cfg(one("A"), regions, st.masks, st.guidance_scale,
+                                                          latents=st.latents.contiguous(), dt_sigma=dt)   # :810-825, :845
+        if st.inject and (st.inject_selfattn > 0 or background_inject_step):                             # :830-841
+            _, st.latents_ref = ops.region_blend_cfg(one("C"), [one("D")], st.ones, st.guidance_scale,
+                                                     latents=st.latents_ref.contiguous(), dt_sigma=dt)
+        if st.use_guidance and float(t) < st.tfd["guidance_start_step"]:                                  # :849
+            st.latents = self._color_guidance(st.latents, st.noise_pred, t, st.tfd)
+        if i == int(st.inject_background * st.n_t) and st.inject_background > 0:                          # :870-872
+            st.latents = ops.bg_inject_blend(st.latents.contiguous(), st.latents_ref.contiguous(), st.masks[-1].contiguous())
+        return st.latents
+
+    def _rich_text_loop(self, ctx, pooled, time_ids, latents, timesteps, guidance_scale, use_guidance,
+                        inject_selfattn, inject_background, tfd, callback, callback_steps):
+        """:772-878."""
+        st = self.prepare_rich_text(ctx, pooled, time_ids, latents, timesteps, guidance_scale, use_guidance,
+                                    inject_selfattn, inject_background, tfd)
         for i, t in enumerate(timesteps):
-            feat_inject_step = bool(float(t) > (1 - inject_selfattn) * 1000)            # :782
-            background_inject_step = i < inject_background * n_t                         # :783
-            sigma = self.scheduler.sigma(t)
-            scale = 1.0 / math.sqrt(sigma * sigma + 1.0)                                 # :784
-            local = plan.local_passes(feat_inject_step)
-            key = tuple(local)
-            if key not in kv_caches:
-                kv_caches[key] = CrossKVCache()
-            rows = [passes[p]["ctx"] for p in local]
-            x = torch.cat([(latents_ref if passes[p]["ref"] else latents) for p in local]) * scale
-            ctrl = RegionControl(kv_cache=kv_caches[key])
-            if feat_inject_step and inject:
-                src = plan.injection_sources(local)                                      # :1018-1061
-                ctrl.qk_src = src
-                ctrl.feature_src = src
-            if word_pos is not None:
-                b_idx = [k for k, p in enumerate(local) if passes[p]["kind"] == "B"]     # :792-797
-                ctrl.word_pos, ctrl.font_size = word_pos, font_size
-                ctrl.fs_batch_mask = sum(1 << k for k in b_idx)
-            eps_local = self.unet(x, t, ctx[rows], {"text_embeds": pooled[rows], "time_ids": time_ids}, ctrl)["sample"]
-            eps = plan.gather(eps_local, local, feat_inject_step)  # [n_passes, 4, h, w]; identity on one GPU
-            kind = {p["kind"] + str(p.get("region", "")): k for k, p in enumerate(passes)}
-            eps_u = eps[kind["A"]:kind["A"] + 1].contiguous()
-            regions = [eps[kind[f"E{j}"]:kind[f"E{j}"] + 1].contiguous() for j in range(N - 1)]
-            regions.append(eps[kind["B"]:kind["B"] + 1].contiguous())
-            dt = self.scheduler.dt(t)
-            noise_pred, latents = ops.region_blend_cfg(eps_u, regions, masks, guidance_scale,
-                                                       latents=latents.contiguous(), dt_sigma=dt)   # :810-825, :845
-            if inject and (inject_selfattn > 0 or background_inject_step):                           # :830-841
-                _, latents_ref = ops.region_blend_cfg(eps[kind["C"]:kind["C"] + 1].contiguous(),
-                                                      [eps[kind["D"]:kind["D"] + 1].contiguous()], ones,
-                                                      guidance_scale, latents=latents_ref.contiguous(), dt_sigma=dt)
-            if use_guidance and float(t) < tfd["guidance_start_step"]:                                # :849
-                latents = self._color_guidance(latents, noise_pred, t, tfd)
-            if i == int(inject_background * n_t) and inject_background > 0:                           # :870-872
-                latents = ops.bg_inject_blend(latents.contiguous(), latents_ref.contiguous(), masks[-1].contiguous())
+            self.rich_text_step(st, i)
             if callback is not None and i % callback_steps == 0:
-                callback(i, t, latents)
-        return latents
+                callback(i, t, st.latents)
+        return st.latents

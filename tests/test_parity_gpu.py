@@ -1,0 +1,269 @@
+"""GPU parity tests proper: the CUDA product path (through the C ABI) against
+  (1) the golden vectors produced by the unmodified reference (tests/golden, fp32 CPU), and
+  (2) the CPU oracle on the same seeded inputs,
+plus size-independent properties at the full SDXL 1024^2 shapes of BASELINE.json.
+
+Stated tolerance (north star: "fp16 per-pixel tolerance"): the product computes in fp16 storage / fp32
+accumulate while the reference vectors are fp32, so
+   UNet noise prediction:   |err| <= 2e-2 + 2e-2*|ref|   per element  (outputs are O(1))
+   latents after k steps:   |err| <= 6e-2 + 3e-2*|ref|   per element  (latents are O(5), guidance 8.5 amplifies)
+   token maps / P-bar:      |err| <= 1e-3 absolute; segment indices bit-exact for identical maps.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _close(got, ref, atol, rtol, what):
+    got = np.asarray(got, dtype=np.float32)
+    ref = np.asarray(ref, dtype=np.float32)
+    err = np.abs(got - ref)
+    tol = atol + rtol * np.abs(ref)
+    assert np.isfinite(got).all(), f"{what}: non-finite values"
+    frac = float((err > tol).mean())
+    assert frac == 0.0, (f"{what}: {frac * 100:.3f}% of elements outside atol={atol} rtol={rtol}; "
+                         f"max err {err.max():.4f} (ref absmax {np.abs(ref).max():.3f}, mean err {err.mean():.5f})")
+    return float(err.max()), float(err.mean())
+
+
+def _product_unet(cfg_oracle, seed):
+    from oracle import unet_oracle as uo
+    from rtti_b200.unet import UNet2DConditionModel, UNetConfig
+    cfg = UNetConfig.from_dict(cfg_oracle.__dict__)
+    unet = UNet2DConditionModel(cfg)
+    unet.load_state_dict(uo.make_state_dict(cfg_oracle, seed))
+    return unet.finalize("cuda")
+
+
+def _pooled(cfg):
+    return cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim if cfg.addition_embed_type else 0
+
+
+@pytest.mark.parametrize("name", ["tiny_sd", "tiny_xl"])
+def test_unet_vs_reference_golden(golden_dir, name):
+    from oracle import unet_oracle as uo
+    cfg = uo.tiny_sd_config() if name == "tiny_sd" else uo.tiny_xl_config()
+    g = _load(golden_dir, f"unet_{name}.npz")
+    unet = _product_unet(cfg, int(g["weight_seed"]))
+    inp = synth.synth_inputs(cfg.cross_attention_dim, _pooled(cfg), 1, int(g["latent"]), int(g["input_seed"]))
+    x = torch.cat([inp["latents"], inp["latents"].flip(-1)]).cuda()
+    added = None
+    if cfg.addition_embed_type:
+        added = {"text_embeds": inp["text_embeds"].cuda(), "time_ids": inp["time_ids"].repeat(2, 1).cuda()}
+    with torch.no_grad():
+        y = unet(x, int(g["timestep"]), inp["ctx"].cuda(), added)["sample"]
+    mx, mean = _close(y.float().cpu().numpy(), g["out"], 2e-2, 2e-2, f"unet {name}")
+    print(f"unet {name}: max err {mx:.4f} mean err {mean:.5f}")
+
+
+def test_attention_vs_reference_golden(golden_dir):
+    """Reference `Attention` module outputs (plain / font-size / injected probabilities / head mean)."""
+    from rtti_b200 import ops
+    g = _load(golden_dir, "attention.npz")
+    heads = 4
+    for tag in ("cross", "self"):
+        W = {k[len(tag) + 3:]: torch.from_numpy(g[k]).cuda().half() for k in g.files if k.startswith(f"{tag}_w_")}
+        hs = torch.from_numpy(g[f"{tag}_hs"]).cuda().half()
+        enc = torch.from_numpy(g[f"{tag}_ctx"]).cuda().half() if tag == "cross" else hs
+        lin = torch.nn.functional.linear
+        q, k, v = lin(hs, W["to_q.weight"]), lin(enc, W["to_k.weight"]), lin(enc, W["to_v.weight"])
+        pbar = torch.zeros(2, hs.shape[1], enc.shape[1], device="cuda") if tag == "cross" else None
+        o = ops.attention(q, k, v, heads, pbar_accum=pbar, cap_slot=[0, 1] if tag == "cross" else None)
+        out = lin(o, W["to_out.0.weight"], W["to_out.0.bias"])
+        _close(out.float().cpu(), g[f"{tag}_out"], 4e-3, 2e-2, f"{tag} attention output")
+        if tag == "cross":
+            _close(pbar.cpu(), g["cross_pavg"], 1e-3, 0, "cross P-bar")
+            pos = torch.tensor([2, 5, 5, 9], dtype=torch.int32, device="cuda")
+            fs = torch.tensor([2.0, 0.5, 3.0, -1.5], device="cuda")
+            pbar.zero_()
+            o = ops.attention(q, k, v, heads, word_pos=pos, font_size=fs, fs_batch_mask=0b11, pbar_accum=pbar, cap_slot=[0, 1])
+            out = lin(o, W["to_out.0.weight"], W["to_out.0.bias"])
+            _close(out.float().cpu(), g["cross_fs_out"], 4e-3, 2e-2, "font-size attention output")
+            _close(pbar.cpu(), g["cross_fs_pavg"], 1e-3, 0, "font-size P-bar")
+        else:
+            # real_attn_probs injection == scores from (q,k) of the stored pass, V from the new hidden states
+            hs2 = torch.from_numpy(g["self_inj_hs"]).cuda().half()
+            v2 = lin(hs2, W["to_v.weight"])
+            qq, kk, vv = torch.cat([q, q]), torch.cat([k, k]), torch.cat([v, v2])
+            o = ops.attention(qq, kk, vv, heads, qk_src=[0, 1, 0, 1])[2:]
+            out = lin(o, W["to_out.0.weight"], W["to_out.0.bias"])
+            _close(out.float().cpu(), g["self_inj_out"], 4e-3, 2e-2, "injected self-attention output")
+
+
+def _xl_model(seed):
+    from oracle import unet_oracle as uo
+    from rtti_b200.region_diffusion_sdxl import RegionDiffusionXL
+    cfg = uo.tiny_xl_config()
+    return cfg, RegionDiffusionXL(device="cuda", unet=_product_unet(cfg, seed), vae=synth.TinyVAE("cuda"))
+
+
+def test_xl_loops_vs_reference_golden(golden_dir):
+    from rtti_b200.attention_utils import cross_maps_mean, self_affinity
+    g = _load(golden_dir, "xl_loops.npz")
+    cfg, model = _xl_model(2)
+    S = 128
+    inp = synth.synth_inputs(cfg.cross_attention_dim, _pooled(cfg), 3, S, 31)
+    ctx, te = inp["ctx"].cuda(), inp["text_embeds"].cuda()
+    # ---- plain pass with capture
+    model.capture_all_resolutions = False
+    model.register_tokenmap_hooks()
+    out = model.sample(height=S * 8, width=S * 8, num_inference_steps=12, guidance_scale=8.5, latents=inp["latents"].clone(),
+                       prompt_embeds=ctx[-1:], negative_prompt_embeds=ctx[:1], pooled_prompt_embeds=te[-1:],
+                       negative_pooled_prompt_embeds=te[:1], output_type="latent", run_rich_text=False)
+    e = _close(out.images.float().cpu(), g["plain_latents"], 6e-2, 3e-2, "xl plain latents")
+    print("xl plain latents err", e)
+    aff = self_affinity(model.selfattn_maps).cpu().numpy()
+    _close(aff[::64], g["plain_aff_rows"], 1e-3, 0, "xl self affinity")
+    assert sorted(model.crossattn_maps) == list(g["plain_cross_names"])
+    _close(cross_maps_mean(model.crossattn_maps).cpu().numpy(), g["plain_cross_mean"], 1e-3, 0, "xl cross maps")
+    assert all(v == 12 for v in model.n_maps.values())
+    model.remove_tokenmap_hooks()
+    # ---- rich loop, everything on
+    model.masks = [m.cuda() for m in inp["masks"]]
+    tfd = synth.font_sizes()
+    tfd.update(synth.color_dict(inp["masks"], S, 1.0))
+    kw = dict(height=S * 8, width=S * 8, num_inference_steps=4, guidance_scale=8.5, prompt_embeds=ctx[1:],
+              negative_prompt_embeds=ctx[:1], pooled_prompt_embeds=te[1:], negative_pooled_prompt_embeds=te[:1],
+              output_type="latent", run_rich_text=True)
+    out = model.sample(latents=inp["latents"].clone(), use_guidance=True, inject_selfattn=0.5, inject_background=0.5,
+                       text_format_dict=tfd, **kw)
+    e = _close(out.images.float().cpu(), g["rich_latents"], 6e-2, 3e-2, "xl rich latents")
+    print("xl rich latents err", e)
+    out = model.sample(latents=inp["latents"].clone(), inject_selfattn=0.0, inject_background=0.5,
+                       text_format_dict={"word_pos": None, "font_size": None}, **kw)
+    e = _close(out.images.float().cpu(), g["rich_bgonly_latents"], 6e-2, 3e-2, "xl bg-only latents")
+    print("xl bg-only latents err", e)
+
+
+def test_sd_loops_vs_reference_golden(golden_dir):
+    from oracle import unet_oracle as uo
+    from rtti_b200.attention_utils import cross_maps_mean, self_affinity
+    from rtti_b200.region_diffusion import RegionDiffusion
+    g = _load(golden_dir, "sd_loops.npz")
+    cfg = uo.tiny_sd_config()
+    S = 64
+    model = RegionDiffusion(device="cuda", unet=_product_unet(cfg, 1), vae=synth.TinyVAE("cuda"))
+    inp = synth.synth_inputs(cfg.cross_attention_dim, 0, 3, S, 21)
+    ctx = inp["ctx"].cuda()
+    model.register_tokenmap_hooks()
+    model.produce_attn_maps(None, None, height=S * 8, width=S * 8, num_inference_steps=12, guidance_scale=8.5,
+                            latents=inp["latents"].clone(), text_embeddings=torch.cat([ctx[:1], ctx[-1:]]), decode=False)
+    assert sorted(model.selfattn_maps) == list(g["plain_self_names"])
+    assert sorted(model.crossattn_maps) == list(g["plain_cross_names"])
+    assert all(v == int(g["plain_ncalls"]) for v in model.n_maps.values())
+    rs = [float(model.selfattn_maps[k][0, 0].sum()) for k in sorted(model.selfattn_maps)]
+    rc = [float(model.crossattn_maps[k][0, 0].sum()) for k in sorted(model.crossattn_maps)]
+    _close(rs, g["plain_self_rowsum"], 5e-3, 0, "sd self row sums (overwrite quirk)")
+    _close(rc, g["plain_cross_rowsum"], 5e-3, 0, "sd cross row sums (3 captured calls)")
+    _close(self_affinity(model.selfattn_maps).cpu().numpy()[::64], g["plain_aff_rows"], 1e-3, 0, "sd self affinity")
+    _close(cross_maps_mean(model.crossattn_maps).cpu().numpy(), g["plain_cross_mean"], 2e-3, 0, "sd cross maps")
+    model.remove_tokenmap_hooks()
+    model.masks = [m.cuda() for m in inp["masks"]]
+    tfd = synth.font_sizes()
+    tfd.update(synth.color_dict(inp["masks"], S, 0.5))
+    lat = model.produce_latents(ctx, height=S * 8, width=S * 8, num_inference_steps=4, guidance_scale=8.5,
+                                latents=inp["latents"].clone(), use_guidance=True, text_format_dict=tfd,
+                                inject_selfattn=0.3, inject_background=0.5)
+    e = _close(lat.float().cpu(), g["rich_latents"], 6e-2, 3e-2, "sd rich latents")
+    print("sd rich latents err", e)
+    lat = model.produce_latents(ctx, height=S * 8, width=S * 8, num_inference_steps=3, guidance_scale=8.5,
+                                latents=inp["latents"].clone(), text_format_dict={"word_pos": None, "font_size": None})
+    e = _close(lat.float().cpu(), g["rich_noinject_latents"], 6e-2, 3e-2, "sd no-inject latents")
+    print("sd no-inject latents err", e)
+
+
+def test_token_maps_vs_reference_golden(golden_dir):
+    """Identical maps in -> bit-exact segment indices -> masks equal to the reference's."""
+    from rtti_b200.attention_utils import get_token_maps
+    g = _load(golden_dir, "token_maps.npz")
+    selfm, crossm = synth.synth_maps(int(g["map_seed"]))
+    selfm = {k: v.cuda() for k, v in selfm.items()}
+    crossm = {k: v.cuda() for k, v in crossm.items()}
+    obj = [torch.LongTensor([3]), torch.LongTensor([7, 8])]
+    masks = get_token_maps(selfm, crossm, None, None, 64, 64, obj, seed=6, segment_threshold=0.3, num_segments=4)
+    got = torch.cat(masks).cpu().numpy()
+    assert got.dtype == np.float32 and got.shape == g["masks"].shape and masks[0].is_cuda
+    _close(got, g["masks"], 1e-5, 0, "token-map masks")
+
+
+def test_step_vs_oracle_batched_equals_sequential():
+    """One rich-text step of the product (one batched UNet call) against the CPU oracle running the
+    reference's sequential pass order, tiny XL model, injection on."""
+    from oracle import sampler_oracle as sam, schedulers_oracle as so, unet_oracle as uo
+    cfg, model = _xl_model(5)
+    S = 128
+    inp = synth.synth_inputs(cfg.cross_attention_dim, _pooled(cfg), 4, S, 41)
+    ctx, te = inp["ctx"], inp["text_embeds"]
+    sch = so.EulerDiscreteSchedulerOracle()
+    sch.set_timesteps(2)
+    lat0 = inp["latents"] * sch.init_noise_sigma
+    ref = sam.rich_text_loop(sam.make_unet_fn(uo.make_state_dict(cfg, 5), cfg), sch, ctx, inp["masks"], lat0.clone(), 2, 8.5,
+                             xl=True, added_cond={"text_embeds": te, "time_ids": inp["time_ids"]},
+                             text_format_dict=synth.font_sizes(), inject_selfattn=0.6, inject_background=0.3)
+    model.masks = [m.cuda() for m in inp["masks"]]
+    out = model.sample(height=S * 8, width=S * 8, num_inference_steps=2, guidance_scale=8.5, latents=inp["latents"].clone(),
+                       prompt_embeds=ctx[1:].cuda(), negative_prompt_embeds=ctx[:1].cuda(), pooled_prompt_embeds=te[1:].cuda(),
+                       negative_pooled_prompt_embeds=te[:1].cuda(), output_type="latent", run_rich_text=True,
+                       inject_selfattn=0.6, inject_background=0.3, text_format_dict=synth.font_sizes())
+    e = _close(out.images.float().cpu(), ref.numpy(), 6e-2, 3e-2, "xl 2-step latents vs oracle")
+    print("xl 2-step vs oracle err", e)
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def test_attention_properties_at_sdxl_shapes():
+    """SDXL 1024^2 attention shapes (64^2 tokens x 10 heads x 64; 32^2 x 20 x 64), size-independent checks:
+    rows of P sum to one (V = 1 -> O = 1), linearity in V, and injection with qk_src == identity is a no-op."""
+    from rtti_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (B, H, T) in ((2, 10, 4096), (3, 20, 1024)):
+        C = H * 64
+        qkv = torch.randn(B, T, 3 * C, device="cuda", generator=g).half()
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        ones = torch.ones(B, T, C, device="cuda", dtype=torch.float16)
+        o1 = ops.attention(q, k, ones, H)
+        assert (o1.float() - 1).abs().max().item() < 2e-3
+        o = ops.attention(q, k, v, H)
+        o2 = ops.attention(q, k, (2 * v.float()).half(), H)
+        assert (o2.float() - 2 * o.float()).abs().max().item() < 4e-3
+        oid = ops.attention(q, k, v, H, qk_src=list(range(B)))
+        assert torch.equal(oid, o)
+        # injection: entry 1 with the scores of entry 0 equals running entry 0's Q,K with entry 1's V
+        src = [0] * B
+        oi = ops.attention(q, k, v, H, qk_src=src)
+        q0 = q[:1].expand(B, -1, -1)
+        k0 = k[:1].expand(B, -1, -1)
+        oj = ops.attention(q0.contiguous(), k0.contiguous(), v.contiguous(), H)
+        assert (oi.float() - oj.float()).abs().max().item() < 1e-3
+        # cross attention, 77 keys: P-bar rows sum to one
+        kc = torch.randn(B, 77, C, device="cuda", generator=g).half()
+        vc = torch.randn(B, 77, C, device="cuda", generator=g).half()
+        pbar = torch.zeros(B, T, 77, device="cuda")
+        ops.attention(q, kc, vc, H, pbar_accum=pbar, cap_slot=list(range(B)))
+        assert (pbar.sum(-1) - 1).abs().max().item() < 2e-3
+
+
+def test_blend_properties_at_sdxl_shapes():
+    from rtti_b200 import ops
+    n = 4 * 128 * 128
+    g = torch.Generator(device="cuda").manual_seed(1)
+    e = torch.randn(n, device="cuda", generator=g).half()
+    m = torch.rand(5, n, device="cuda", generator=g)
+    m = m / m.sum(0, keepdim=True)
+    # all passes equal -> eps unchanged whatever the guidance (masks sum to one)
+    out = ops.region_blend_cfg(e, [e] * 5, m, 8.5)
+    assert (out.float() - e.float()).abs().max().item() < 5e-3
+    # guidance 1 -> plain masked text prediction
+    er = [torch.randn(n, device="cuda", generator=g).half() for _ in range(5)]
+    out = ops.region_blend_cfg(e, er, m, 1.0)
+    ref = sum(x.float() * mm for x, mm in zip(er, m))
+    assert (out.float() - ref).abs().max().item() < 5e-3
