@@ -127,6 +127,25 @@ int rtti_bg_inject_blend(const void* latents, const void* latents_ref, const flo
 /* x0 = (x_t - eps * sqrt(1-alpha)) / sqrt(alpha)   (models/region_diffusion_sdxl.py:955-957). fp16. */
 int rtti_predict_x0(const void* x_t, const void* eps, float alpha, void* x0, long long n, void* stream);
 
+/* Multi-GPU region parallelism (new relative to the single-GPU reference loop,
+ * models/region_diffusion_sdxl.py:779-845): fused all-gather + region blend + CFG + Euler update over NVLink
+ * peer memory. Every rank calls it once per step on its own stream after writing the noise predictions of
+ * the passes it owns into its slot buffer.
+ *   peer_slots (host, [world]): device pointers, valid on THIS device, to each rank's slot buffer
+ *       fp16 [2 (step parity)][n_slots][n]; slot 0 = unconditional pass, slots 1..n_regions = region passes
+ *       in mask order (base-prompt pass last), slot n_regions+1 / +2 = reference-latent uncond / base passes.
+ *   peer_flags (host, [world]): device pointers to each rank's uint32 step counter (zero-initialised).
+ *   slot_owner (host, [n_slots]): rank that writes slot s.  step_id: 1, 2, 3, ... identical on all ranks.
+ *   Outputs are written locally on every rank (replicated, bit-identical): eps_out [n]; latents_out =
+ *   latents + dt_sigma*eps; latents_ref_out = latents_ref + dt_sigma*(eps_C + guidance*(eps_D - eps_C)).
+ *   latents/latents_out and latents_ref/latents_ref_out may be NULL pairs.
+ */
+int rtti_gather_blend_step(const void* const* peer_slots, void* const* peer_flags, int world, int rank,
+                           const int* slot_owner, int n_slots, int n_regions, const float* masks, long long n,
+                           float guidance, void* eps_out, const void* latents, void* latents_out,
+                           const void* latents_ref, void* latents_ref_out, float dt_sigma, unsigned int step_id,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

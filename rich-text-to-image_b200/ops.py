@@ -240,3 +240,24 @@ def predict_x0(x_t, eps, alpha):
                "rtti_predict_x0")
     _count(1)
     return out
+
+
+def gather_blend_step(peer_slot_ptrs, peer_flag_ptrs, rank, slot_owner, n_regions, masks, guidance, latents, latents_ref,
+                      dt_sigma, step_id):
+    """Fused all-gather + blend + CFG + Euler over NVLink peer memory (rtti_gather_blend_step).
+    Returns (eps, latents_out, latents_ref_out or None)."""
+    lib = _lib.load()
+    world = len(peer_slot_ptrs)
+    n = latents.numel()
+    _req(latents, _F16, "latents"); _req(masks, torch.float32, "masks")
+    eps = torch.empty_like(latents)
+    lat_out = torch.empty_like(latents)
+    ref_out = torch.empty_like(latents_ref) if latents_ref is not None else None
+    slots = (ctypes.c_void_p * world)(*peer_slot_ptrs)
+    flags = (ctypes.c_void_p * world)(*peer_flag_ptrs)
+    rc = lib.rtti_gather_blend_step(slots, flags, world, rank, _int_array(slot_owner), len(slot_owner), n_regions,
+                                    _ptr(masks), n, float(guidance), _ptr(eps), _ptr(latents), _ptr(lat_out),
+                                    _ptr(latents_ref), _ptr(ref_out), float(dt_sigma), int(step_id), _stream())
+    _lib.check(rc, "rtti_gather_blend_step")
+    _count(1)
+    return eps, lat_out, ref_out

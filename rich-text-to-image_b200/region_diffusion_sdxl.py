@@ -59,6 +59,8 @@ class RegionDiffusionXL:
         self.n_maps = None
         self._capture = None
         self.capture_all_resolutions = False
+        self._exchanges = {}
+        self.fused_exchange = True   # multi-GPU: fused peer-memory gather+blend kernel instead of NCCL all-gather
         self.last_step_stats = {}
 
     @classmethod
@@ -261,15 +263,30 @@ class RegionDiffusionXL:
             ctrl.word_pos, ctrl.font_size = st.word_pos, st.font_size                   # :792-797
             ctrl.fs_batch_mask = sum(1 << k for k, p in enumerate(local) if passes[p]["kind"] == "B")
         eps_local = self.unet(x, t, st.ctx[rows], {"text_embeds": st.pooled[rows], "time_ids": st.time_ids}, ctrl)["sample"]
-        eps = plan.gather(eps_local, local, feat_inject_step)   # [n_passes, 4, h, w]; identity on one GPU
-        one = lambda name: eps[kind[name]:kind[name] + 1].contiguous()
-        regions = [one(f"E{j}") for j in range(N - 1)] + [one("B")]
         dt = self.scheduler.dt(t)
-        st.noise_pred, st.latents = ops.region_blend_cfg(one("A"), regions, st.masks, st.guidance_scale,
-                                                          latents=st.latents.contiguous(), dt_sigma=dt)   # :810-825, :845
-        if st.inject and (st.inject_selfattn > 0 or background_inject_step):                             # :830-841
-            _, st.latents_ref = ops.region_blend_cfg(one("C"), [one("D")], st.ones, st.guidance_scale,
-                                                     latents=st.latents_ref.contiguous(), dt_sigma=dt)
+        step_ref = st.inject and (st.inject_selfattn > 0 or background_inject_step)                       # :830-841
+        if plan.world > 1 and self.fused_exchange:
+            # fused all-gather + blend + CFG + Euler over NVLink peer memory (csrc/gather_blend.cu)
+            xkey = (tuple(p["kind"] for p in passes), st.latents[0].numel())
+            if xkey not in self._exchanges:   # symmetric buffers are allocated once per problem shape
+                self._exchanges[xkey] = region_parallel.PeerExchange(passes, st.latents[0].numel(), self.device)
+            ex = self._exchanges[xkey]
+            _, owner = plan._plan(feat_inject_step)
+            sid = ex.publish(eps_local, local, owner)
+            st.noise_pred, st.latents, ref_out = ops.gather_blend_step(
+                ex.slot_ptrs, ex.flag_ptrs, ex.rank, ex.slot_owner(owner), N, st.masks, st.guidance_scale,
+                st.latents.contiguous(), st.latents_ref.contiguous() if step_ref else None, dt, sid)
+            if step_ref:
+                st.latents_ref = ref_out
+        else:
+            eps = plan.gather(eps_local, local, feat_inject_step)   # NCCL all-gather; identity on one GPU
+            one = lambda name: eps[kind[name]:kind[name] + 1].contiguous()
+            regions = [one(f"E{j}") for j in range(N - 1)] + [one("B")]
+            st.noise_pred, st.latents = ops.region_blend_cfg(one("A"), regions, st.masks, st.guidance_scale,
+                                                              latents=st.latents.contiguous(), dt_sigma=dt)   # :810-825, :845
+            if step_ref:
+                _, st.latents_ref = ops.region_blend_cfg(one("C"), [one("D")], st.ones, st.guidance_scale,
+                                                         latents=st.latents_ref.contiguous(), dt_sigma=dt)
         if st.use_guidance and float(t) < st.tfd["guidance_start_step"]:                                  # :849
             st.latents = self._color_guidance(st.latents, st.noise_pred, t, st.tfd)
         if i == int(st.inject_background * st.n_t) and st.inject_background > 0:                          # :870-872

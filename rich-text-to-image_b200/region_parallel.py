@@ -114,3 +114,55 @@ class RegionParallelPlan:
             r = owner[p]
             out[p] = parts[r][assign[r].index(p)]
         return out
+
+
+class PeerExchange:
+    """Symmetric (peer-mapped) slot buffers for the fused gather+blend kernel (csrc/gather_blend.cu).
+
+    Layout per rank: [256 B header: uint32 step flag][fp16 slots [2 parities][n_slots][n]].  The buffers are
+    allocated with torch's symmetric memory (CUDA IPC / multicast-capable allocation, NVLink peer access);
+    PyTorch is used for the rendezvous only — the exchange itself is the kernel's peer loads.
+    Slot order: 0 = A (uncond), 1..N-1 = E_1..E_{N-1}, N = B (base), N+1 = C, N+2 = D."""
+    HEADER = 256
+
+    def __init__(self, passes, n, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.dist = dist
+        self.group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n = n
+        n_regions = sum(1 for p in passes if p["kind"] == "E") + 1
+        self.n_regions = n_regions
+        has_ref = any(p["kind"] == "C" for p in passes)
+        self.n_slots = n_regions + 1 + (2 if has_ref else 0)
+        self.slot_of_pass = []
+        for p in passes:
+            k = p["kind"]
+            self.slot_of_pass.append({"A": 0, "B": n_regions, "C": n_regions + 1, "D": n_regions + 2}.get(k, 1 + p.get("region", 0)))
+        nbytes = self.HEADER + 2 * self.n_slots * n * 2
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.handle = symm.rendezvous(self.buf, self.group.group_name)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+        base = [int(p) for p in self.handle.buffer_ptrs]
+        self.flag_ptrs = base
+        self.slot_ptrs = [b + self.HEADER for b in base]
+        self.slots = self.buf[self.HEADER:].view(torch.float16).view(2, self.n_slots, n)
+        self.step_id = 0
+
+    def publish(self, eps_local, local, owner):
+        """Copy the noise predictions of the passes this rank OWNS into its slots for the next step id."""
+        self.step_id += 1
+        par = self.step_id & 1
+        for k, p in enumerate(local):
+            if owner[p] == self.rank:
+                self.slots[par, self.slot_of_pass[p]].copy_(eps_local[k].reshape(-1))
+        return self.step_id
+
+    def slot_owner(self, owner):
+        out = [0] * self.n_slots
+        for p, s in enumerate(self.slot_of_pass):
+            out[s] = owner[p]
+        return out

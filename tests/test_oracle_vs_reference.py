@@ -1,0 +1,67 @@
+"""CPU, build container only: the oracle against the UNMODIFIED reference imported through oracle/ref_shim.py
+on inputs other than the committed fixtures. Skipped where /root/reference does not exist (the GPU box)."""
+import pytest
+import torch
+
+from oracle import ref_shim, unet_oracle as uo
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import torchvision  # noqa: F401  (before the stub modules are installed)
+    return ref_shim.import_reference()
+
+
+@pytest.mark.parametrize("cfg_fn,seed", [(uo.tiny_sd_config, 3), (uo.tiny_xl_config, 4)])
+def test_unet_forward_bit_exact(ref, cfg_fn, seed):
+    cfg = cfg_fn()
+    sd = uo.make_state_dict(cfg, seed)
+    model = ref.unet_2d_condition.UNet2DConditionModel(**cfg.ref_kwargs())
+    model.load_state_dict(sd)
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == {k: tuple(v) for k, v in uo.param_shapes(cfg).items()}
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(2, 4, 16, 16, generator=g)
+    ctx = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    added = None
+    if cfg.addition_embed_type:
+        pooled = cfg.projection_class_embeddings_input_dim - 6 * cfg.addition_time_embed_dim
+        added = {"text_embeds": torch.randn(2, pooled, generator=g), "time_ids": torch.tensor([[128.0, 128, 0, 0, 128, 128]] * 2)}
+    with torch.no_grad():
+        for t in (torch.tensor(999), torch.tensor(37.0, dtype=torch.float64)):
+            yr = model(x, t, encoder_hidden_states=ctx, added_cond_kwargs=added)["sample"]
+            yo = uo.unet_forward(sd, cfg, x, t, ctx, added)
+            assert torch.equal(yr, yo)
+
+
+def test_full_size_parameter_inventories(ref):
+    for cfg, nparams in ((uo.sd15_config(), 859.5e6), (uo.sdxl_config(), 2567.5e6)):
+        with torch.device("meta"):
+            model = ref.unet_2d_condition.UNet2DConditionModel(**cfg.ref_kwargs())
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        mine = {k: tuple(v) for k, v in uo.param_shapes(cfg).items()}
+        assert shapes == mine
+        assert abs(sum(torch.Size(s).numel() for s in mine.values()) - nparams) < 0.1e6
+
+
+def test_attention_fontsize_and_injection(ref):
+    torch.manual_seed(0)
+    attn = ref.attention_processor.Attention(query_dim=64, cross_attention_dim=48, heads=2, dim_head=32)
+    sd = {"a." + k: v for k, v in attn.state_dict().items()}
+    hs, ctx = torch.randn(1, 32, 64), torch.randn(1, 77, 48)
+    aw = {"word_pos": torch.LongTensor([1, 4, 4]), "font_size": torch.FloatTensor([3.0, -2.0, 0.25])}
+
+    class C(uo.AttnControl):
+        def pre_attn(self, name):
+            return None, aw
+
+        def post_attn(self, name, pavg, p):
+            self.out = (pavg, p)
+
+    c = C()
+    with torch.no_grad():
+        o_ref, (pavg_ref, p_ref) = attn(hs, None, aw, encoder_hidden_states=ctx)
+        o = uo.attention(sd, "a", 2, hs, ctx, c)
+    assert torch.allclose(o, o_ref, atol=1e-6) and torch.allclose(c.out[0], pavg_ref, atol=1e-7)
+    assert torch.allclose(c.out[1], p_ref, atol=1e-7)
