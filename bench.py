@@ -103,11 +103,23 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def host_threads():
+    """CPU threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(math.ceil(int(quota) / int(period)))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_oracle_pass_time(n_passes, warm):
-    """Seconds per batch-1 SDXL UNet pass of the CPU oracle (fp32, all host threads)."""
+    """Seconds per batch-1 SDXL UNet pass of the CPU oracle (fp32, all usable host threads)."""
     import torch
     from oracle import unet_oracle as uo
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     cfg = uo.sdxl_config()
     g = torch.Generator().manual_seed(0)
     sd = {}
@@ -191,8 +203,10 @@ def run_product(args, rank, world, local_rank):
         launches0 = ops.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        torch.cuda.nvtx.range_push("timed")
         for i in range(args.warmup, args.warmup + args.steps):
             model.rich_text_step(st, i % NUM_INFERENCE_STEPS)
+        torch.cuda.nvtx.range_pop()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -234,10 +248,13 @@ def run_product(args, rank, world, local_rank):
     roof = None
     if rank == 0:
         ops.PROFILE = []
+        model.profile_events = {}
         with torch.no_grad():
             model.rich_text_step(st, (args.warmup + args.steps) % NUM_INFERENCE_STEPS)
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
+        breakdown = {k: a.elapsed_time(b) for k, (a, b) in model.profile_events.items()}
+        model.profile_events = None
         hbm, tf_burst, tf_sust, src = peaks()
         agg = {}
         for ev0, ev1, kind, flops, nbytes, shape in prof:
@@ -274,7 +291,7 @@ def run_product(args, rank, world, local_rank):
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": args.steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "last_color_loss": loss},
-        "roofline": roof, "roofline_cross_attention": cross,
+        "roofline": roof, "roofline_cross_attention": cross, "breakdown_ms": breakdown,
     }
     if world == 1 and not args.no_cpu_baseline:
         per_pass, threads = cpu_oracle_pass_time(1, 0)

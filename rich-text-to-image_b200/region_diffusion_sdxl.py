@@ -60,6 +60,7 @@ class RegionDiffusionXL:
         self._capture = None
         self.capture_all_resolutions = False
         self._exchanges = {}
+        self.profile_events = None   # dict -> CUDA-event pairs per phase of a step (bench.py breakdown)
         self.fused_exchange = True   # multi-GPU: fused peer-memory gather+blend kernel instead of NCCL all-gather
         self.last_step_stats = {}
 
@@ -262,7 +263,13 @@ class RegionDiffusionXL:
         if st.word_pos is not None:
             ctrl.word_pos, ctrl.font_size = st.word_pos, st.font_size                   # :792-797
             ctrl.fs_batch_mask = sum(1 << k for k, p in enumerate(local) if passes[p]["kind"] == "B")
+        pe = self.profile_events
+        if pe is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         eps_local = self.unet(x, t, st.ctx[rows], {"text_embeds": st.pooled[rows], "time_ids": st.time_ids}, ctrl)["sample"]
+        if pe is not None:
+            ev[1].record()
         dt = self.scheduler.dt(t)
         step_ref = st.inject and (st.inject_selfattn > 0 or background_inject_step)                       # :830-841
         if plan.world > 1 and self.fused_exchange:
@@ -287,10 +294,15 @@ class RegionDiffusionXL:
             if step_ref:
                 _, st.latents_ref = ops.region_blend_cfg(one("C"), [one("D")], st.ones, st.guidance_scale,
                                                          latents=st.latents_ref.contiguous(), dt_sigma=dt)
+        if pe is not None:
+            ev[2].record()
         if st.use_guidance and float(t) < st.tfd["guidance_start_step"]:                                  # :849
             st.latents = self._color_guidance(st.latents, st.noise_pred, t, st.tfd)
         if i == int(st.inject_background * st.n_t) and st.inject_background > 0:                          # :870-872
             st.latents = ops.bg_inject_blend(st.latents.contiguous(), st.latents_ref.contiguous(), st.masks[-1].contiguous())
+        if pe is not None:
+            ev[3].record()
+            pe.update(unet=(ev[0], ev[1]), exchange_blend=(ev[1], ev[2]), color_guidance=(ev[2], ev[3]))
         return st.latents
 
     def _rich_text_loop(self, ctx, pooled, time_ids, latents, timesteps, guidance_scale, use_guidance,
