@@ -232,7 +232,8 @@ def run_product(args, rank, world, local_rank):
         t0 = time.perf_counter()
         for i in range(args.warmup, args.warmup + args.steps):
             s2 = fresh_state(pinned)                 # H2D of this step's inputs from pinned host memory
-            s2.kv_caches = st.kv_caches              # prompt K/V projections are per-prompt state, kept across steps
+            s2.kv_caches = st.kv_caches              # prompt K/V projections and the captured UNet graphs are
+            s2.graphs = st.graphs                    # per-prompt state, kept across steps
             model.rich_text_step(s2, i % NUM_INFERENCE_STEPS)   # the public step call
             host_lat.copy_(s2.latents, non_blocking=False)      # D2H of the step result
             loss = float(model.last_step_stats["color_loss"].item())
@@ -249,11 +250,20 @@ def run_product(args, rank, world, local_rank):
     if rank == 0:
         ops.PROFILE = []
         model.profile_events = {}
+        graphs_on, model.use_cuda_graphs = model.use_cuda_graphs, False   # eager so every launch carries its events
         with torch.no_grad():
             model.rich_text_step(st, (args.warmup + args.steps) % NUM_INFERENCE_STEPS)
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         breakdown = {k: a.elapsed_time(b) for k, (a, b) in model.profile_events.items()}
+        breakdown["note"] = "eager (no CUDA graph) profiling step"
+        model.profile_events = None
+        model.use_cuda_graphs = graphs_on
+        model.profile_events = {}
+        with torch.no_grad():
+            model.rich_text_step(st, (args.warmup + args.steps + 1) % NUM_INFERENCE_STEPS)
+        torch.cuda.synchronize()
+        breakdown_graph = {k: a.elapsed_time(b) for k, (a, b) in model.profile_events.items()}
         model.profile_events = None
         hbm, tf_burst, tf_sust, src = peaks()
         agg = {}
@@ -291,7 +301,7 @@ def run_product(args, rank, world, local_rank):
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": args.steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "last_color_loss": loss},
-        "roofline": roof, "roofline_cross_attention": cross, "breakdown_ms": breakdown,
+        "roofline": roof, "roofline_cross_attention": cross, "breakdown_ms": breakdown_graph, "breakdown_eager_ms": breakdown,
     }
     if world == 1 and not args.no_cpu_baseline:
         per_pass, threads = cpu_oracle_pass_time(1, 0)

@@ -127,6 +127,18 @@ int rtti_bg_inject_blend(const void* latents, const void* latents_ref, const flo
 /* x0 = (x_t - eps * sqrt(1-alpha)) / sqrt(alpha)   (models/region_diffusion_sdxl.py:955-957). fp16. */
 int rtti_predict_x0(const void* x_t, const void* eps, float alpha, void* x0, long long n, void* stream);
 
+/* fp32 channels-last GroupNorm(+SiLU) forward / input-gradient backward for the VAE decoder that colour guidance
+ * differentiates through (third-party AutoencoderKL, called at models/region_diffusion_sdxl.py:856-865 and
+ * models/region_diffusion.py:157-165). x, y, dz, dx: [batch, hw, c] fp32; gamma/beta [c] fp32;
+ * mean_rstd [batch, groups, 2] fp32 (written by fwd, read by bwd); workspace fp32
+ * [rtti_gn32_workspace_elems(...)]. dx = d loss / d x given dz = d loss / d (silu?(GN(x))).
+ */
+long long rtti_gn32_workspace_elems(int batch, int hw, int c, int groups);
+int rtti_gn32_silu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd,
+                       float* workspace, int batch, int hw, int c, int groups, float eps, int apply_silu, void* stream);
+int rtti_gn32_silu_bwd(const float* x, const float* dz, const float* gamma, const float* beta, const float* mean_rstd,
+                       float* dx, float* workspace, int batch, int hw, int c, int groups, int apply_silu, void* stream);
+
 /* Multi-GPU region parallelism (new relative to the single-GPU reference loop,
  * models/region_diffusion_sdxl.py:779-845): fused all-gather + region blend + CFG + Euler update over NVLink
  * peer memory. Every rank calls it once per step on its own stream after writing the noise predictions of

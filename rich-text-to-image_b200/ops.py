@@ -261,3 +261,47 @@ def gather_blend_step(peer_slot_ptrs, peer_flag_ptrs, rank, slot_owner, n_region
     _lib.check(rc, "rtti_gather_blend_step")
     _count(1)
     return eps, lat_out, ref_out
+
+
+_gn32_ws = {}
+
+
+def _gn32_workspace(x, groups):
+    lib = _lib.load()
+    B, HW, C = x.shape
+    n = lib.rtti_gn32_workspace_elems(B, HW, C, groups)
+    key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _gn32_ws.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 1 << 18), dtype=torch.float32, device=x.device)
+        _gn32_ws[key] = ws
+    return ws
+
+
+def gn32_silu_fwd(x, gamma, beta, groups, eps, silu):
+    """fp32 channels-last GroupNorm(+SiLU): x [B, HW, C] -> (y, mean_rstd [B, G, 2])  (rtti_gn32_silu_fwd)."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    assert x.dim() == 3 and x.is_contiguous()
+    B, HW, C = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
+    rc = lib.rtti_gn32_silu_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), _ptr(_gn32_workspace(x, groups)),
+                                B, HW, C, groups, float(eps), 1 if silu else 0, _stream())
+    _lib.check(rc, "rtti_gn32_silu_fwd")
+    _count(3)
+    return y, stats
+
+
+def gn32_silu_bwd(x, dz, gamma, beta, stats, groups, silu):
+    """Input gradient of gn32_silu_fwd (rtti_gn32_silu_bwd)."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x"); _req(dz, torch.float32, "dz")
+    assert x.is_contiguous() and dz.is_contiguous() and dz.shape == x.shape
+    B, HW, C = x.shape
+    dx = torch.empty_like(x)
+    rc = lib.rtti_gn32_silu_bwd(_ptr(x), _ptr(dz), _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(dx),
+                                _ptr(_gn32_workspace(x, groups)), B, HW, C, groups, 1 if silu else 0, _stream())
+    _lib.check(rc, "rtti_gn32_silu_bwd")
+    _count(3)
+    return dx

@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from . import ops, region_parallel
+from . import ops, region_parallel, vae_guidance
 from .attention_utils import CrossAttentionLayers, SelfAttentionLayers
 from .schedulers import PNDMScheduler
 from .unet import CrossKVCache, RegionControl, TokenMapAccumulator, UNet2DConditionModel, UNetConfig
@@ -85,16 +85,17 @@ class RegionDiffusion:
     def _color_guidance(self, latents, noise_pred, t, tfd):
         """:151-168."""
         x0, alpha = self.predict_x0(latents, noise_pred, t)
-        z = ((1 / 0.18215) * x0.float()).requires_grad_(True)
-        with torch.enable_grad():
-            dec = self.vae.decode_tensor(z)
         masks = torch.stack([m[0, 0].to(self.device, torch.float32) for m in tfd["color_obj_atten"]]).contiguous()
         tgt = torch.stack([r.reshape(3).to(self.device, torch.float32) for r in tfd["target_RGB"]]).contiguous()
-        loss, g = ops.color_loss_fwd_bwd(dec.detach()[0].contiguous(), masks, tgt)
-        dec.backward(g[None])
-        grad_lat = z.grad * ((1 / 0.18215) / math.sqrt(alpha))
+
+        def grad_image(img):
+            loss, g = ops.color_loss_fwd_bwd(img[0].contiguous(), masks, tgt)
+            self.last_step_stats["color_loss"] = loss
+            return g[None]
+
+        grad_lat = vae_guidance.image_and_latent_grad(self.vae, (1 / 0.18215) * x0.float(), grad_image) \
+            * ((1 / 0.18215) / math.sqrt(alpha))
         atten_all = tfd["color_obj_atten_all"].to(self.device, torch.float32).expand_as(grad_lat).contiguous()
-        self.last_step_stats["color_loss"] = loss
         return ops.latent_guidance_update(latents.contiguous(), grad_lat.contiguous(), atten_all,
                                           float(tfd["color_guidance_weight"]))
 

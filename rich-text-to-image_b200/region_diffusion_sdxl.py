@@ -18,7 +18,7 @@ from typing import List, Optional
 import numpy as np
 import torch
 
-from . import ops, region_parallel
+from . import ops, region_parallel, vae_guidance
 from .attention_utils import CrossAttentionLayers_XL
 from .schedulers import EulerDiscreteScheduler
 from .unet import CrossKVCache, RegionControl, TokenMapAccumulator, UNet2DConditionModel, UNetConfig
@@ -60,6 +60,8 @@ class RegionDiffusionXL:
         self._capture = None
         self.capture_all_resolutions = False
         self._exchanges = {}
+        self.use_cuda_graphs = True  # replay the batched UNet pass of a step as one CUDA graph (launch-bound otherwise)
+        self._graph_pool = None
         self.profile_events = None   # dict -> CUDA-event pairs per phase of a step (bench.py breakdown)
         self.fused_exchange = True   # multi-GPU: fused peer-memory gather+blend kernel instead of NCCL all-gather
         self.last_step_stats = {}
@@ -116,17 +118,16 @@ class RegionDiffusionXL:
         rtti_color_loss_fwd_bwd and the VAE (third-party) in PyTorch autograd with frozen weights."""
         x0, alpha = self.predict_x0(latents, noise_pred, t)
         sf = self.vae.config.scaling_factor
-        z = (x0.float() / sf).requires_grad_(True)
-        with torch.enable_grad():
-            dec = self.vae.decode_tensor(z)
         masks = torch.stack([m[0, 0].to(self.device, torch.float32) for m in tfd["color_obj_atten"]]).contiguous()
         tgt = torch.stack([r.reshape(3).to(self.device, torch.float32) for r in tfd["target_RGB"]]).contiguous()
-        dec_c = dec.detach()[0].contiguous()
-        loss, g = ops.color_loss_fwd_bwd(dec_c, masks, tgt)
-        dec.backward(g[None].contiguous(memory_format=torch.channels_last) if dec.is_contiguous(memory_format=torch.channels_last) else g[None])
-        grad_lat = z.grad / (sf * math.sqrt(alpha))
+
+        def grad_image(img):
+            loss, g = ops.color_loss_fwd_bwd(img[0].contiguous(), masks, tgt)
+            self.last_step_stats["color_loss"] = loss
+            return g[None]
+
+        grad_lat = vae_guidance.image_and_latent_grad(self.vae, x0.float() / sf, grad_image) / (sf * math.sqrt(alpha))
         atten_all = tfd["color_obj_atten_all"].to(self.device, torch.float32).expand_as(grad_lat).contiguous()
-        self.last_step_stats["color_loss"] = loss
         return ops.latent_guidance_update(latents.contiguous(), grad_lat.contiguous(), atten_all,
                                           float(tfd["color_guidance_weight"]))
 
@@ -240,8 +241,59 @@ class RegionDiffusionXL:
         else:
             st.word_pos = st.font_size = None
         st.kv_caches = {}
+        st.graphs = {}
         st.noise_pred = None
         return st
+
+    def _unet_pass(self, st, x, t, local, feat_inject_step):
+        """The batched UNet call of one step: eager, or (use_cuda_graphs) captured once per batch composition
+        and replayed — the pass is ~1400 kernel launches whose CPU launch cost exceeds their GPU time."""
+        passes, plan = st.passes, st.plan
+        rows = [passes[p]["ctx"] for p in local]
+        inj = bool(feat_inject_step and st.inject)
+        key = (tuple(local), inj)
+        kvc = st.kv_caches.setdefault(tuple(local), CrossKVCache())
+
+        def make_ctrl():
+            ctrl = RegionControl(kv_cache=kvc)
+            if inj:
+                src = plan.injection_sources(local)                                     # :1018-1061
+                ctrl.qk_src = src
+                ctrl.feature_src = src
+                ctrl.feature_idx = st.graphs.setdefault(("idx",) + key, torch.as_tensor(src, device=self.device))
+            if st.word_pos is not None:
+                ctrl.word_pos, ctrl.font_size = st.word_pos, st.font_size               # :792-797
+                ctrl.fs_batch_mask = sum(1 << k for k, p in enumerate(local) if passes[p]["kind"] == "B")
+            return ctrl
+
+        if not self.use_cuda_graphs:
+            return self.unet(x, t, st.ctx[rows], {"text_embeds": st.pooled[rows], "time_ids": st.time_ids}, make_ctrl())["sample"]
+        g = st.graphs.get(key)
+        if g is None:
+            g = {"x": torch.empty_like(x), "t": torch.zeros(1, dtype=torch.float32, device=self.device),
+                 "ctx": st.ctx[rows].contiguous(), "added": {"text_embeds": st.pooled[rows].contiguous(), "time_ids": st.time_ids}}
+            g["x"].copy_(x)
+            g["t"].fill_(float(t))
+            run = lambda: self.unet(g["x"], g["t"], g["ctx"], g["added"], make_ctrl())["sample"]
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):      # warm-up outside capture: fills the prompt K/V cache, sets func attributes
+                run()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES
+            with torch.cuda.graph(graph, pool=self._graph_pool):
+                g["out"] = run()
+            g["launches"] = ops.LAUNCHES - n0   # rtti kernels inside the graph (for the launch accounting)
+            if self._graph_pool is None:
+                self._graph_pool = graph.pool()
+            g["graph"] = graph
+            st.graphs[key] = g
+        g["x"].copy_(x)
+        g["t"].fill_(float(t))
+        g["graph"].replay()
+        ops._count(g["launches"])
+        return g["out"]
 
     def rich_text_step(self, st, i):
         """One iteration of the region loop, models/region_diffusion_sdxl.py:779-878."""
@@ -252,22 +304,12 @@ class RegionDiffusionXL:
         sigma = self.scheduler.sigma(t)
         scale = 1.0 / math.sqrt(sigma * sigma + 1.0)                                    # :784
         local = plan.local_passes(feat_inject_step)
-        kvc = st.kv_caches.setdefault(tuple(local), CrossKVCache())
-        rows = [passes[p]["ctx"] for p in local]
         x = torch.cat([(st.latents_ref if passes[p]["ref"] else st.latents) for p in local]) * scale
-        ctrl = RegionControl(kv_cache=kvc)
-        if feat_inject_step and st.inject:
-            src = plan.injection_sources(local)                                         # :1018-1061
-            ctrl.qk_src = src
-            ctrl.feature_src = src
-        if st.word_pos is not None:
-            ctrl.word_pos, ctrl.font_size = st.word_pos, st.font_size                   # :792-797
-            ctrl.fs_batch_mask = sum(1 << k for k, p in enumerate(local) if passes[p]["kind"] == "B")
         pe = self.profile_events
         if pe is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
-        eps_local = self.unet(x, t, st.ctx[rows], {"text_embeds": st.pooled[rows], "time_ids": st.time_ids}, ctrl)["sample"]
+        eps_local = self._unet_pass(st, x, t, local, feat_inject_step)
         if pe is not None:
             ev[1].record()
         dt = self.scheduler.dt(t)

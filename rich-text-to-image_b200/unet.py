@@ -133,6 +133,7 @@ class RegionControl:
     """Per-call description of what the reference does with hooks around each UNet pass."""
     qk_src: Optional[List[int]] = None          # self-attn injection: entry b uses Q,K of entry qk_src[b]
     feature_src: Optional[List[int]] = None     # up_blocks.1.resnets.1 hidden-state injection, same indexing
+    feature_idx: Optional[torch.Tensor] = None  # the same as a device int64 tensor (avoids an H2D copy per call)
     word_pos: Optional[torch.Tensor] = None     # int32 [n]  (font-size re-weighting, attn2 only)
     font_size: Optional[torch.Tensor] = None    # fp32 [n]
     fs_batch_mask: int = 0                      # bit b set -> entry b gets the re-weighting (pass B only)
@@ -299,16 +300,16 @@ class ResnetBlock2D(nn.Module):
         self.conv2 = Conv2dCL(cout, cout, 3, padding=1)
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
-    def forward(self, x, H, W, temb_act, feature_src=None):
+    def forward(self, x, H, W, temb_act, feature_idx=None):
         """x [B, HW, Cin]; temb_act = silu(temb). Returns output [B, HW, Cout] (resnet.py:591-645)."""
         h = self.norm1(x, silu=True)
         h, _, _ = self.conv1.forward_cl(h, H, W)
         t = F.linear(temb_act, self.time_emb_proj.weight, self.time_emb_proj.bias)
         h = self.norm2(h, silu=True, chan_bias=t.contiguous())  # `hidden_states + temb` fused into the norm
         h, _, _ = self.conv2.forward_cl(h, H, W)
-        if feature_src is not None:
+        if feature_idx is not None:
             # inject_states of the reference pass replaces the residual branch (resnet.py:639-641)
-            h = h.index_select(0, torch.as_tensor(feature_src, device=h.device))
+            h = h.index_select(0, feature_idx)
         if self.conv_shortcut is not None:
             x = F.linear(x, self.conv_shortcut.weight.view(self.conv_shortcut.weight.shape[0], -1), self.conv_shortcut.bias)
         return h.add_(x)
@@ -456,6 +457,9 @@ class UNet2DConditionModel(nn.Module):
             emb = emb + mlp(self.add_embedding, add)
         temb_act = F.silu(emb)
         ctx = _f16(encoder_hidden_states).contiguous()
+        feat_idx = ctrl.feature_idx
+        if feat_idx is None and ctrl.feature_src is not None:
+            feat_idx = torch.as_tensor(ctrl.feature_src, device=dev)
 
         x = _f16(sample).permute(0, 2, 3, 1).contiguous().view(B, H * W, -1)
         h, H, W = self.conv_in.forward_cl(x, H, W)
@@ -477,7 +481,7 @@ class UNet2DConditionModel(nn.Module):
                 s, _, _ = skips.pop()
                 h = torch.cat([h, s], dim=-1)
                 rname = f"up_blocks.{i}.resnets.{l}"
-                h = res(h, H, W, temb_act, ctrl.feature_src if rname == FEATURE_INJECT_RESNET else None)
+                h = res(h, H, W, temb_act, feat_idx if rname == FEATURE_INJECT_RESNET else None)
                 if blk.has_cross_attention:
                     h = blk.attentions[l](h, ctx, ctrl, f"up_blocks.{i}.attentions.{l}")
             if blk.upsamplers is not None:
