@@ -23,6 +23,8 @@
 //   warp  4    TMA producer (one elected lane)
 //   warp  5    tcgen05.mma issuer (one lane) + TMEM allocator
 // TMEM columns: S/P at [0,128) (P is written back in place as packed fp16), O at [128, 128+64*NDCH).
+#include <stdlib.h>
+
 #include "ptx.cuh"
 #include "rtti_internal.h"
 
@@ -52,17 +54,19 @@ struct AttnCfg {
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NQBUF * NDCH * Q_TILE;
   static constexpr int OFF_V = OFF_K + NSTAGE * NDCH * KV_TILE;
-  static constexpr int OFF_O = OFF_V + NSTAGE * NDCH * KV_TILE;
-  static constexpr int OFF_BAR = OFF_O + NDCH * Q_TILE;
+  // KT == 64 (3 CTAs/SM): the output staging tile aliases the Q tile (one head per CTA, Q is dead by then)
+  static constexpr int OFF_O = (KT == 64) ? OFF_Q : OFF_V + NSTAGE * NDCH * KV_TILE;
+  static constexpr int OFF_BAR = (KT == 64) ? OFF_V + NSTAGE * NDCH * KV_TILE : OFF_O + NDCH * Q_TILE;
   static constexpr int OFF_FS = OFF_BAR + 256;
   static constexpr int SMEM_BYTES = OFF_FS + 128 * 4 + 1024 /*alignment slack*/;
-  static constexpr uint32_t TMEM_COLS = (128 + 64 * NDCH) <= 256 ? 256 : 512;
-  static constexpr int MIN_CTAS = (NDCH == 1 && !CAPTURE) ? 2 : 1;
-  static constexpr uint32_t O_COL = 128;
+  static constexpr uint32_t O_COL = (KT == 64) ? 64 : 128;
+  static constexpr uint32_t TMEM_COLS = (KT == 64) ? 128 : ((128 + 64 * NDCH) <= 256 ? 256 : 512);
+  static constexpr int MIN_CTAS = (KT == 64) ? 3 : ((NDCH == 1 && !CAPTURE) ? 2 : 1);
+  static constexpr int MAX_REGS = MIN_CTAS == 3 ? 112 : (MIN_CTAS == 2 ? 168 : 255);
 };
 
 template <int KT, int NDCH, bool CAPTURE>
-__global__ void __launch_bounds__(192, (AttnCfg<KT, NDCH, CAPTURE>::MIN_CTAS))
+__global__ void __launch_bounds__(192) __maxnreg__((AttnCfg<KT, NDCH, CAPTURE>::MAX_REGS))
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                 const AttnParams p) {
@@ -253,6 +257,60 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_before();
         mbar_arrive(p_full);
         ++tit;
+      } else if constexpr (KT == 64) {
+        // ---- key tiles of 64, three CTAs per SM: the 64-column row of S lives in registers (one TMEM round trip)
+        for (int j = 0; j < p.n_k_tiles; ++j, ++tit) {
+          mbar_wait(s_full, tit & 1);
+          tc_fence_after();
+          const int valid = p.n_k - j * KT;
+          float s[64];
+          tmem_ld32(tlane, reinterpret_cast<uint32_t*>(s));
+          tmem_ld32(tlane + 32, reinterpret_cast<uint32_t*>(s) + 32);
+          tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s));
+          tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s) + 32);
+          if (valid < KT) {
+#pragma unroll
+            for (int i = 0; i < KT; ++i)
+              if (i >= valid) s[i] = -INFINITY;
+          }
+          float mx = s[0];
+#pragma unroll
+          for (int i = 1; i < KT; ++i) mx = fmaxf(mx, s[i]);
+          const float mxs = mx * p.scale_log2;
+          if (j == 0) {
+            m_ref = mxs;
+          } else {
+            const bool need = mxs > m_ref + 8.f;
+            if (__any_sync(0xffffffffu, need)) {
+              const float alpha = need ? ex2_approx(m_ref - mxs) : 1.f;
+              if (need) m_ref = mxs;
+              l *= alpha;
+#pragma unroll
+              for (int c = 0; c < 4 * NDCH; ++c) {  // 16 columns at a time: the S row stays live in registers
+                uint32_t o[16];
+                tmem_ld16(tlane + C::O_COL + 16 * c, o);
+                tmem_wait_ld_regs16(o);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st16(tlane + C::O_COL + 16 * c, o);
+              }
+            }
+          }
+          float rowsum = 0.f;
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e0 = ex2_approx(fmaf(s[2 * i], p.scale_log2, -m_ref));
+            const float e1 = ex2_approx(fmaf(s[2 * i + 1], p.scale_log2, -m_ref));
+            rowsum += e0 + e1;
+            pk[i] = pack_half2(e0, e1);
+          }
+          l += rowsum;
+          tmem_st32(tlane, pk);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(p_full);
+        }
       } else {
         // ---- key tiles of 128 with online softmax; S is streamed from TMEM twice (max, then exp)
         //      in 32-column chunks so the row never has to live in registers.
@@ -409,6 +467,9 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 
 using namespace rtti;
 
+// A/B switch for profiling: RTTI_ATTN_KT128=1 in the environment keeps the 128-key-tile kernel for head_dim <= 64.
+static const bool g_force_kt128 = [] { const char* e = getenv("RTTI_ATTN_KT128"); return e && e[0] == '1'; }();
+
 extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads,
                              int head_dim, int n_q, int n_k, long long q_bs, long long q_rs, long long k_bs,
                              long long k_rs, long long v_bs, long long v_rs, long long o_bs, long long o_rs,
@@ -427,12 +488,21 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
   int rc = rtti_arch_ok();
   if (rc != RTTI_OK) return rc;
 
-  const int KT = (n_k <= 80) ? 80 : 128;
   const int ndch = (head_dim + 63) / 64;
+  // 77 text keys: one 80-key tile.  head_dim <= 64: 64-key tiles, 3 CTAs per SM.  else 128-key tiles.
+  const int KT = (n_k <= 80) ? 80 : ((ndch == 1 && !g_force_kt128) ? 64 : 128);
   AttnParams p{};
   p.batch = batch; p.heads = heads; p.head_dim = head_dim; p.n_q = n_q; p.n_k = n_k;
   p.n_k_tiles = (n_k + KT - 1) / KT;
   p.heads_per_cta = want_cap ? heads : 1;
+  if (!want_cap && KT == 80) {
+    // cross-attention: several heads per CTA so the TMA loads of head h+1 overlap the softmax/epilogue of
+    // head h (double-buffered Q/K/V), while keeping at least two CTAs per SM worth of work
+    const long long ctas1 = (long long)((n_q + 127) / 128) * heads * batch;
+    const int cand[] = {10, 8, 5, 4, 2};
+    for (int c : cand)
+      if (heads % c == 0 && ctas1 / c >= 296) { p.heads_per_cta = c; break; }
+  }
   p.ksteps_qk = (head_dim + 15) / 16;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.inv_heads = 1.f / (float)heads;
@@ -468,6 +538,7 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
     if (ndch == 2) RTTI_LAUNCH(80, 2, false);
     RTTI_LAUNCH(80, 3, false);
   }
+  if (KT == 64) RTTI_LAUNCH(64, 1, false);
   if (ndch == 1) RTTI_LAUNCH(128, 1, false);
   if (ndch == 2) RTTI_LAUNCH(128, 2, false);
   RTTI_LAUNCH(128, 3, false);

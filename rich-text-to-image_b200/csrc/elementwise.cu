@@ -40,11 +40,11 @@ static GNPlan gn_plan(int batch, int hw, int c) {
   p.rowlanes = p.nvec >= 256 ? 1 : (256 / p.nvec);
   if (p.rowlanes < 1) p.rowlanes = 1;
   p.threads = p.nvec * p.rowlanes;
-  int want = (592 + batch - 1) / batch;                 // ~4 CTAs per SM across the batch
+  int want = (1184 + batch - 1) / batch;                // ~8 CTAs per SM across the batch
   int maxc = (hw + p.rowlanes * 4 - 1) / (p.rowlanes * 4);  // at least 4 rows per thread
   if (maxc < 1) maxc = 1;
   p.chunks = want < maxc ? want : maxc;
-  if (p.chunks > 128) p.chunks = 128;
+  if (p.chunks > 256) p.chunks = 256;
   if (p.chunks < 1) p.chunks = 1;
   p.rows_per_chunk = (hw + p.chunks - 1) / p.chunks;
   p.rows_per_chunk = ((p.rows_per_chunk + p.rowlanes - 1) / p.rowlanes) * p.rowlanes;
@@ -66,13 +66,29 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __re
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; tb[i] = 0.f; }
   if (chan_bias) unpack8(*reinterpret_cast<const Half8*>(chan_bias + (size_t)b * c + vec * 8), tb);
   const __half* base = x + ((size_t)b * hw) * c + vec * 8;
-  for (int r = r0 + rl; r < r1; r += rowlanes) {
+  int r = r0 + rl;
+  for (; r + 3 * rowlanes < r1; r += 4 * rowlanes) {  // 4 independent 128-bit loads in flight per thread
+    Half8 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const Half8*>(base + (size_t)(r + u * rowlanes) * c);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = f[i] + tb[i];
+        s[i] += t; ss[i] += t * t;
+      }
+    }
+  }
+  for (; r < r1; r += rowlanes) {
     float f[8];
     unpack8(*reinterpret_cast<const Half8*>(base + (size_t)r * c), f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float v = f[i] + tb[i];
-      s[i] += v; ss[i] += v * v;
+      const float t = f[i] + tb[i];
+      s[i] += t; ss[i] += t * t;
     }
   }
 #pragma unroll
@@ -101,17 +117,29 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __re
   extern __shared__ float sm[];  // [groups][2] mean, rstd
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int cpg = c / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    float a = 0.f, q = 0.f;
-    for (int k = 0; k < chunks; ++k) {
-      const float* o = ws + (((size_t)b * chunks + k) * groups + g) * 2;
-      a += o[0]; q += o[1];
+  {
+    // one warp per group: lanes stride over the chunk partials, fixed-order shuffle tree (deterministic)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+    const bool full_warp = (warp + 1) * 32 <= (int)blockDim.x;
+    if (full_warp) {
+      const int nfull = blockDim.x >> 5;
+      for (int g = warp; g < groups; g += nfull) {
+        float a = 0.f, q = 0.f;
+        for (int k = lane; k < chunks; k += 32) {
+          const float* o = ws + (((size_t)b * chunks + k) * groups + g) * 2;
+          a += o[0]; q += o[1];
+        }
+        a = warp_sum(a); q = warp_sum(q);
+        if (lane == 0) {
+          const float n = (float)hw * (float)cpg;
+          const float mean = a / n;
+          const float var = fmaxf(q / n - mean * mean, 0.f);
+          sm[2 * g] = mean;
+          sm[2 * g + 1] = rsqrtf(var + eps);
+        }
+      }
     }
-    const float n = (float)hw * (float)cpg;
-    const float mean = a / n;
-    const float var = fmaxf(q / n - mean * mean, 0.f);
-    sm[2 * g] = mean;
-    sm[2 * g + 1] = rsqrtf(var + eps);
+    (void)nwarps;
   }
   __syncthreads();
   const int vec = threadIdx.x % nvec, rl = threadIdx.x / nvec;
@@ -130,13 +158,30 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __re
   const int r0 = chunk * rows_per_chunk;
   const int r1 = min(hw, r0 + rows_per_chunk);
   const size_t base = ((size_t)b * hw) * c + vec * 8;
-  for (int r = r0 + rl; r < r1; r += rowlanes) {
+  int r = r0 + rl;
+  for (; r + 3 * rowlanes < r1; r += 4 * rowlanes) {
+    Half8 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const Half8*>(x + base + (size_t)(r + u * rowlanes) * c);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = fmaf(f[i], sc[i], sh[i]);
+        f[i] = apply_silu ? silu(t) : t;
+      }
+      *reinterpret_cast<Half8*>(y + base + (size_t)(r + u * rowlanes) * c) = pack8(f);
+    }
+  }
+  for (; r < r1; r += rowlanes) {
     float f[8];
     unpack8(*reinterpret_cast<const Half8*>(x + base + (size_t)r * c), f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float v = fmaf(f[i], sc[i], sh[i]);
-      f[i] = apply_silu ? silu(v) : v;
+      const float t = fmaf(f[i], sc[i], sh[i]);
+      f[i] = apply_silu ? silu(t) : t;
     }
     *reinterpret_cast<Half8*>(y + base + (size_t)r * c) = pack8(f);
   }
@@ -147,44 +192,52 @@ template <int VPL>  // vectors (8 halfs) per lane
 __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                                  const __half* __restrict__ beta, __half* __restrict__ y, int rows, int c,
                                  float eps) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int nvec = c / 8;
-  const __half* xr = x + (size_t)warp * c;
-  float f[VPL][8];
-  float sum = 0.f;
+  float ga[VPL][8], be[VPL][8];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const int v = lane + 32 * k;
     if (v < nvec) {
-      unpack8(*reinterpret_cast<const Half8*>(xr + v * 8), f[k]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sum += f[k][i];
+      unpack8(*reinterpret_cast<const Half8*>(gamma + v * 8), ga[k]);
+      unpack8(*reinterpret_cast<const Half8*>(beta + v * 8), be[k]);
     }
   }
-  const float mean = warp_sum(sum) / (float)c;
-  float sq = 0.f;
+  const float inv_c = 1.f / (float)c;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps_total) {
+    const __half* xr = x + (size_t)row * c;
+    Half8 raw[VPL];
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int v = lane + 32 * k;
-    if (v < nvec) {
+    for (int k = 0; k < VPL; ++k)
+      if (lane + 32 * k < nvec) raw[k] = *reinterpret_cast<const Half8*>(xr + (lane + 32 * k) * 8);
+    float f[VPL][8];
+    float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = f[k][i] - mean; sq += d * d; }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)c + eps);
-  __half* yr = y + (size_t)warp * c;
+    for (int k = 0; k < VPL; ++k)
+      if (lane + 32 * k < nvec) {
+        unpack8(raw[k], f[k]);
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int v = lane + 32 * k;
-    if (v < nvec) {
-      float ga[8], be[8], o[8];
-      unpack8(*reinterpret_cast<const Half8*>(gamma + v * 8), ga);
-      unpack8(*reinterpret_cast<const Half8*>(beta + v * 8), be);
+        for (int i = 0; i < 8; ++i) sum += f[k][i];
+      }
+    const float mean = warp_sum(sum) * inv_c;
+    float sq = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * ga[i] + be[i];
-      *reinterpret_cast<Half8*>(yr + v * 8) = pack8(o);
-    }
+    for (int k = 0; k < VPL; ++k)
+      if (lane + 32 * k < nvec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = f[k][i] - mean; sq += d * d; }
+      }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_c + eps);
+    __half* yr = y + (size_t)row * c;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+      if (lane + 32 * k < nvec) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * ga[k][i] + be[k][i];
+        *reinterpret_cast<Half8*>(yr + (lane + 32 * k) * 8) = pack8(o);
+      }
   }
 }
 
@@ -392,7 +445,8 @@ extern "C" int rtti_layernorm_fwd(const void* x, const void* gamma, const void* 
   if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) return RTTI_ERR_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const int vpl = (c / 8 + 31) / 32;
-  const int blocks = (rows + 7) / 8;
+  int blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;  // persistent warps stride over the rows
 #define LN(V) layernorm_kernel<V><<<blocks, 256, 0, st>>>((const __half*)x, (const __half*)gamma, (const __half*)beta, (__half*)y, rows, c, eps)
   if (vpl <= 1) LN(1); else if (vpl <= 2) LN(2); else if (vpl <= 3) LN(3); else if (vpl <= 4) LN(4);
   else if (vpl <= 5) LN(5); else if (vpl <= 6) LN(6); else LN(8);

@@ -260,7 +260,10 @@ class RegionDiffusionXL:
                 src = plan.injection_sources(local)                                     # :1018-1061
                 ctrl.qk_src = src
                 ctrl.feature_src = src
-                ctrl.feature_idx = st.graphs.setdefault(("idx",) + key, torch.as_tensor(src, device=self.device))
+                ikey = ("idx",) + key
+                if ikey not in st.graphs:   # built once, outside any capture
+                    st.graphs[ikey] = torch.as_tensor(src, device=self.device)
+                ctrl.feature_idx = st.graphs[ikey]
             if st.word_pos is not None:
                 ctrl.word_pos, ctrl.font_size = st.word_pos, st.font_size               # :792-797
                 ctrl.fs_batch_mask = sum(1 << k for k, p in enumerate(local) if passes[p]["kind"] == "B")

@@ -23,9 +23,10 @@ def main():
     t_dev = torch.full((1,), 981.0, device=dev)
     kv = CrossKVCache()
     src = [0, 1, 2, 3] + [3] * (B - 4) if B > 4 else None
+    idx = torch.as_tensor(src, device=dev) if src else None
 
     def run():
-        ctrl = RegionControl(kv_cache=kv, qk_src=src, feature_src=src)
+        ctrl = RegionControl(kv_cache=kv, qk_src=src, feature_src=src, feature_idx=idx)
         return unet(x, t_dev, ctx, added, ctrl)["sample"]
 
     with torch.no_grad():
