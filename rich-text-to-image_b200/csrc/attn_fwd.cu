@@ -467,8 +467,8 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 
 using namespace rtti;
 
-// A/B switch for profiling: RTTI_ATTN_KT128=1 in the environment keeps the 128-key-tile kernel for head_dim <= 64.
-static const bool g_force_kt128 = [] { const char* e = getenv("RTTI_ATTN_KT128"); return e && e[0] == '1'; }();
+// A/B switch for profiling: RTTI_ATTN_KT64=1 selects the 64-key-tile / 3-CTA-per-SM kernel for head_dim <= 64.
+static const bool g_use_kt64 = [] { const char* e = getenv("RTTI_ATTN_KT64"); return e && e[0] == '1'; }();
 
 extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads,
                              int head_dim, int n_q, int n_k, long long q_bs, long long q_rs, long long k_bs,
@@ -489,8 +489,9 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
   if (rc != RTTI_OK) return rc;
 
   const int ndch = (head_dim + 63) / 64;
-  // 77 text keys: one 80-key tile.  head_dim <= 64: 64-key tiles, 3 CTAs per SM.  else 128-key tiles.
-  const int KT = (n_k <= 80) ? 80 : ((ndch == 1 && !g_force_kt128) ? 64 : 128);
+  // 77 text keys: one 80-key tile; otherwise 128-key tiles (2 CTAs/SM). The 64-key / 3-CTA variant measured
+  // 15 % slower on B200 (profiles/r01_kernels_*.jsonl) and is kept behind RTTI_ATTN_KT64=1 for experiments.
+  const int KT = (n_k <= 80) ? 80 : ((ndch == 1 && g_use_kt64) ? 64 : 128);
   AttnParams p{};
   p.batch = batch; p.heads = heads; p.head_dim = head_dim; p.n_q = n_q; p.n_k = n_k;
   p.n_k_tiles = (n_k + KT - 1) / KT;

@@ -40,11 +40,11 @@ static GNPlan gn_plan(int batch, int hw, int c) {
   p.rowlanes = p.nvec >= 256 ? 1 : (256 / p.nvec);
   if (p.rowlanes < 1) p.rowlanes = 1;
   p.threads = p.nvec * p.rowlanes;
-  int want = (1184 + batch - 1) / batch;                // ~8 CTAs per SM across the batch
+  int want = (592 + batch - 1) / batch;                 // ~4 CTAs per SM across the batch
   int maxc = (hw + p.rowlanes * 4 - 1) / (p.rowlanes * 4);  // at least 4 rows per thread
   if (maxc < 1) maxc = 1;
   p.chunks = want < maxc ? want : maxc;
-  if (p.chunks > 256) p.chunks = 256;
+  if (p.chunks > 128) p.chunks = 128;
   if (p.chunks < 1) p.chunks = 1;
   p.rows_per_chunk = (hw + p.chunks - 1) / p.chunks;
   p.rows_per_chunk = ((p.rows_per_chunk + p.rowlanes - 1) / p.rowlanes) * p.rowlanes;
@@ -110,38 +110,34 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __re
   }
 }
 
+// one warp per (batch, group): fixed-order reduction of the chunk partials -> (mean, rstd)
+__global__ void gn_finalize_kernel(const float* __restrict__ ws, float* __restrict__ mean_rstd, int groups, int chunks,
+                                   float n, float eps) {
+  const int b = blockIdx.y;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= groups) return;
+  float a = 0.f, q = 0.f;
+  for (int k = lane; k < chunks; k += 32) {
+    const float* o = ws + (((size_t)b * chunks + k) * groups + g) * 2;
+    a += o[0]; q += o[1];
+  }
+  a = warp_sum(a); q = warp_sum(q);
+  if (lane == 0) {
+    const float mean = a / n;
+    const float var = fmaxf(q / n - mean * mean, 0.f);
+    mean_rstd[((size_t)b * groups + g) * 2] = mean;
+    mean_rstd[((size_t)b * groups + g) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
 __global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ chan_bias,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
-                                const float* __restrict__ ws, __half* __restrict__ y, int hw, int c, int groups,
-                                int nvec, int rowlanes, int rows_per_chunk, int chunks, float eps, int apply_silu) {
-  extern __shared__ float sm[];  // [groups][2] mean, rstd
+                                const float* __restrict__ mean_rstd, __half* __restrict__ y, int hw, int c, int groups,
+                                int nvec, int rowlanes, int rows_per_chunk, int apply_silu) {
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int cpg = c / groups;
-  {
-    // one warp per group: lanes stride over the chunk partials, fixed-order shuffle tree (deterministic)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
-    const bool full_warp = (warp + 1) * 32 <= (int)blockDim.x;
-    if (full_warp) {
-      const int nfull = blockDim.x >> 5;
-      for (int g = warp; g < groups; g += nfull) {
-        float a = 0.f, q = 0.f;
-        for (int k = lane; k < chunks; k += 32) {
-          const float* o = ws + (((size_t)b * chunks + k) * groups + g) * 2;
-          a += o[0]; q += o[1];
-        }
-        a = warp_sum(a); q = warp_sum(q);
-        if (lane == 0) {
-          const float n = (float)hw * (float)cpg;
-          const float mean = a / n;
-          const float var = fmaxf(q / n - mean * mean, 0.f);
-          sm[2 * g] = mean;
-          sm[2 * g + 1] = rsqrtf(var + eps);
-        }
-      }
-    }
-    (void)nwarps;
-  }
-  __syncthreads();
+  const float* sm = mean_rstd + (size_t)b * groups * 2;  // written by gn_finalize_kernel
   const int vec = threadIdx.x % nvec, rl = threadIdx.x / nvec;
   float sc[8], sh[8], ga[8], be[8], tb[8];
   unpack8(*reinterpret_cast<const Half8*>(gamma + vec * 8), ga);
@@ -188,56 +184,48 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __re
 }
 
 // ============================================================================ LayerNorm
-template <int VPL>  // vectors (8 halfs) per lane
+template <int VPL>  // vectors (8 halfs) per lane; one warp per row (measured faster than persistent warps)
 __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                                  const __half* __restrict__ beta, __half* __restrict__ y, int rows, int c,
                                  float eps) {
-  const int lane = threadIdx.x & 31;
-  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
   const int nvec = c / 8;
-  float ga[VPL][8], be[VPL][8];
+  const __half* xr = x + (size_t)warp * c;
+  Half8 raw[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+    if (lane + 32 * k < nvec) raw[k] = *reinterpret_cast<const Half8*>(xr + (lane + 32 * k) * 8);
+  float f[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+    if (lane + 32 * k < nvec) {
+      unpack8(raw[k], f[k]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += f[k][i];
+    }
+  const float mean = warp_sum(sum) / (float)c;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+    if (lane + 32 * k < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[k][i] - mean; sq += d * d; }
+    }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)c + eps);
+  __half* yr = y + (size_t)warp * c;
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const int v = lane + 32 * k;
     if (v < nvec) {
-      unpack8(*reinterpret_cast<const Half8*>(gamma + v * 8), ga[k]);
-      unpack8(*reinterpret_cast<const Half8*>(beta + v * 8), be[k]);
+      float ga[8], be[8], o[8];
+      unpack8(*reinterpret_cast<const Half8*>(gamma + v * 8), ga);
+      unpack8(*reinterpret_cast<const Half8*>(beta + v * 8), be);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * ga[i] + be[i];
+      *reinterpret_cast<Half8*>(yr + v * 8) = pack8(o);
     }
-  }
-  const float inv_c = 1.f / (float)c;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps_total) {
-    const __half* xr = x + (size_t)row * c;
-    Half8 raw[VPL];
-#pragma unroll
-    for (int k = 0; k < VPL; ++k)
-      if (lane + 32 * k < nvec) raw[k] = *reinterpret_cast<const Half8*>(xr + (lane + 32 * k) * 8);
-    float f[VPL][8];
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < VPL; ++k)
-      if (lane + 32 * k < nvec) {
-        unpack8(raw[k], f[k]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sum += f[k][i];
-      }
-    const float mean = warp_sum(sum) * inv_c;
-    float sq = 0.f;
-#pragma unroll
-    for (int k = 0; k < VPL; ++k)
-      if (lane + 32 * k < nvec) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { const float d = f[k][i] - mean; sq += d * d; }
-      }
-    const float rstd = rsqrtf(warp_sum(sq) * inv_c + eps);
-    __half* yr = y + (size_t)row * c;
-#pragma unroll
-    for (int k = 0; k < VPL; ++k)
-      if (lane + 32 * k < nvec) {
-        float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * ga[k][i] + be[k][i];
-        *reinterpret_cast<Half8*>(yr + (lane + 32 * k) * 8) = pack8(o);
-      }
   }
 }
 
@@ -410,7 +398,7 @@ using namespace rtti;
 extern "C" long long rtti_groupnorm_workspace_elems(int batch, int hw, int c, int groups) {
   if (batch < 1 || hw < 1 || c < 8 || groups < 1) return 0;
   const GNPlan p = gn_plan(batch, hw, c);
-  return (long long)batch * p.chunks * groups * 2;
+  return (long long)batch * p.chunks * groups * 2 + (long long)batch * groups * 2;
 }
 
 extern "C" int rtti_groupnorm_silu_fwd(const void* x, const void* chan_bias, const void* gamma, const void* beta,
@@ -431,9 +419,12 @@ extern "C" int rtti_groupnorm_silu_fwd(const void* x, const void* chan_bias, con
   dim3 grid(p.chunks, batch);
   gn_stats_kernel<<<grid, p.threads, sm1, st>>>((const __half*)x, (const __half*)chan_bias, workspace, hw, c, groups,
                                                 p.nvec, p.rowlanes, p.rows_per_chunk, p.chunks);
-  gn_apply_kernel<<<grid, p.threads, groups * 2 * sizeof(float), st>>>(
-      (const __half*)x, (const __half*)chan_bias, (const __half*)gamma, (const __half*)beta, workspace, (__half*)y,
-      hw, c, groups, p.nvec, p.rowlanes, p.rows_per_chunk, p.chunks, eps, apply_silu);
+  float* mean_rstd = workspace + (size_t)batch * p.chunks * groups * 2;
+  gn_finalize_kernel<<<dim3((groups + 7) / 8, batch), 256, 0, st>>>(workspace, mean_rstd, groups, p.chunks,
+                                                                    (float)hw * (float)(c / groups), eps);
+  gn_apply_kernel<<<grid, p.threads, 0, st>>>((const __half*)x, (const __half*)chan_bias, (const __half*)gamma,
+                                              (const __half*)beta, mean_rstd, (__half*)y, hw, c, groups, p.nvec,
+                                              p.rowlanes, p.rows_per_chunk, apply_silu);
   return ok_or_cuda();
 }
 
@@ -445,8 +436,7 @@ extern "C" int rtti_layernorm_fwd(const void* x, const void* gamma, const void* 
   if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) return RTTI_ERR_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const int vpl = (c / 8 + 31) / 32;
-  int blocks = (rows + 7) / 8;
-  if (blocks > 148 * 8) blocks = 148 * 8;  // persistent warps stride over the rows
+  const int blocks = (rows + 7) / 8;
 #define LN(V) layernorm_kernel<V><<<blocks, 256, 0, st>>>((const __half*)x, (const __half*)gamma, (const __half*)beta, (__half*)y, rows, c, eps)
   if (vpl <= 1) LN(1); else if (vpl <= 2) LN(2); else if (vpl <= 3) LN(3); else if (vpl <= 4) LN(4);
   else if (vpl <= 5) LN(5); else if (vpl <= 6) LN(6); else LN(8);

@@ -135,7 +135,7 @@ def groupnorm_silu(x, gamma, beta, groups, eps, silu, chan_bias=None, out=None):
     rc = lib.rtti_groupnorm_silu_fwd(_ptr(x), _ptr(chan_bias), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(ws), B, HW, C,
                                      groups, float(eps), 1 if silu else 0, _stream())
     _lib.check(rc, "rtti_groupnorm_silu_fwd")
-    _count(2)
+    _count(3)
     return out
 
 

@@ -61,7 +61,6 @@ class RegionDiffusionXL:
         self.capture_all_resolutions = False
         self._exchanges = {}
         self.use_cuda_graphs = True  # replay the batched UNet pass of a step as one CUDA graph (launch-bound otherwise)
-        self._graph_pool = None
         self.profile_events = None   # dict -> CUDA-event pairs per phase of a step (bench.py breakdown)
         self.fused_exchange = True   # multi-GPU: fused peer-memory gather+blend kernel instead of NCCL all-gather
         self.last_step_stats = {}
@@ -285,11 +284,11 @@ class RegionDiffusionXL:
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES
-            with torch.cuda.graph(graph, pool=self._graph_pool):
+            with torch.cuda.graph(graph, pool=st.graphs.get("pool")):
                 g["out"] = run()
             g["launches"] = ops.LAUNCHES - n0   # rtti kernels inside the graph (for the launch accounting)
-            if self._graph_pool is None:
-                self._graph_pool = graph.pool()
+            if "pool" not in st.graphs:   # the graphs of one sampling call share a memory pool
+                st.graphs["pool"] = graph.pool()
             g["graph"] = graph
             st.graphs[key] = g
         g["x"].copy_(x)
