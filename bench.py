@@ -246,25 +246,25 @@ def run_product(args, rank, world, local_rank):
     d2h = host_lat.numel() * 2 + 4
 
     # ------------------------------------------------------------- roofline of the dominant rtti kernel (CUDA events)
-    roof = None
+    # (every rank executes the profiling steps: on >1 GPU each step contains the cross-rank exchange)
+    roof = cross = None
+    ops.PROFILE = []
+    model.profile_events = {}
+    graphs_on, model.use_cuda_graphs = model.use_cuda_graphs, False   # eager so every launch carries its events
+    with torch.no_grad():
+        model.rich_text_step(st, (args.warmup + args.steps) % NUM_INFERENCE_STEPS)
+    barrier()
+    prof, ops.PROFILE = ops.PROFILE, None
+    breakdown = {k: a.elapsed_time(b) for k, (a, b) in model.profile_events.items()}
+    breakdown["note"] = "eager (no CUDA graph) profiling step"
+    model.use_cuda_graphs = graphs_on
+    model.profile_events = {}
+    with torch.no_grad():
+        model.rich_text_step(st, (args.warmup + args.steps + 1) % NUM_INFERENCE_STEPS)
+    barrier()
+    breakdown_graph = {k: a.elapsed_time(b) for k, (a, b) in model.profile_events.items()}
+    model.profile_events = None
     if rank == 0:
-        ops.PROFILE = []
-        model.profile_events = {}
-        graphs_on, model.use_cuda_graphs = model.use_cuda_graphs, False   # eager so every launch carries its events
-        with torch.no_grad():
-            model.rich_text_step(st, (args.warmup + args.steps) % NUM_INFERENCE_STEPS)
-        torch.cuda.synchronize()
-        prof, ops.PROFILE = ops.PROFILE, None
-        breakdown = {k: a.elapsed_time(b) for k, (a, b) in model.profile_events.items()}
-        breakdown["note"] = "eager (no CUDA graph) profiling step"
-        model.profile_events = None
-        model.use_cuda_graphs = graphs_on
-        model.profile_events = {}
-        with torch.no_grad():
-            model.rich_text_step(st, (args.warmup + args.steps + 1) % NUM_INFERENCE_STEPS)
-        torch.cuda.synchronize()
-        breakdown_graph = {k: a.elapsed_time(b) for k, (a, b) in model.profile_events.items()}
-        model.profile_events = None
         hbm, tf_burst, tf_sust, src = peaks()
         agg = {}
         for ev0, ev1, kind, flops, nbytes, shape in prof:
@@ -278,7 +278,6 @@ def run_product(args, rank, world, local_rank):
                     "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust, "traffic": None,
                     "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                     "launches_timed": s[3], "ms_per_step_in_kernel": s[0] * 1e3}
-        cross = None
         if c:
             gbs = c[2] / c[0] / 1e9
             cross = {"kernel": "attn_fwd_kernel<80,1> (cross-attention, 77 keys)", "bound": "hbm", "achieved": gbs,

@@ -45,7 +45,7 @@ struct AttnParams {
   float* lse;   // [batch, heads, n_q] fp32, log2-domain log-sum-exp of the scaled scores (optional)
 };
 
-template <int KT, int NDCH, bool CAPTURE>
+template <int KT, int NDCH, bool CAPTURE, bool EXP16 = false>
 struct AttnCfg {
   static constexpr int NQBUF = (KT == 80 && NDCH < 3) ? 2 : 1;
   static constexpr int NSTAGE = (KT == 128 && NDCH == 3) ? 1 : 2;
@@ -58,19 +58,23 @@ struct AttnCfg {
   static constexpr int OFF_O = (KT == 64) ? OFF_Q : OFF_V + NSTAGE * NDCH * KV_TILE;
   static constexpr int OFF_BAR = (KT == 64) ? OFF_V + NSTAGE * NDCH * KV_TILE : OFF_O + NDCH * Q_TILE;
   static constexpr int OFF_FS = OFF_BAR + 256;
-  static constexpr int SMEM_BYTES = OFF_FS + 128 * 4 + 1024 /*alignment slack*/;
+  // EXP16: a 2 KB all-ones fp16 tile = B operand of the row-sum MMA (L += P * 1), 1024-aligned
+  static constexpr int OFF_ONES = ((OFF_FS + 128 * 4 + 1023) / 1024) * 1024;
+  static constexpr int SMEM_BYTES = (EXP16 ? OFF_ONES + 2048 : OFF_FS + 128 * 4) + 1024 /*alignment slack*/;
   static constexpr uint32_t O_COL = (KT == 64) ? 64 : 128;
+  static constexpr uint32_t L_COL = O_COL + 64 * NDCH;  // EXP16: 16 columns holding the running row sum
   static constexpr uint32_t TMEM_COLS = (KT == 64) ? 128 : ((128 + 64 * NDCH) <= 256 ? 256 : 512);
   static constexpr int MIN_CTAS = (KT == 64) ? 3 : ((NDCH == 1 && !CAPTURE) ? 2 : 1);
   static constexpr int MAX_REGS = MIN_CTAS == 3 ? 112 : (MIN_CTAS == 2 ? 168 : 255);
 };
 
-template <int KT, int NDCH, bool CAPTURE>
-__global__ void __launch_bounds__(192) __maxnreg__((AttnCfg<KT, NDCH, CAPTURE>::MAX_REGS))
+template <int KT, int NDCH, bool CAPTURE, bool EXP16 = false>
+__global__ void __launch_bounds__(192) __maxnreg__((AttnCfg<KT, NDCH, CAPTURE, EXP16>::MAX_REGS))
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                 const AttnParams p) {
-  using C = AttnCfg<KT, NDCH, CAPTURE>;
+  using C = AttnCfg<KT, NDCH, CAPTURE, EXP16>;
+  static_assert(!EXP16 || (KT == 128 && NDCH == 1), "EXP16 path: 128-key tiles, head_dim <= 64");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -105,6 +109,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // dense signed weight per key; duplicates in word_pos: last write wins, as the reference's
     // advanced-index assignment does on CPU (attention_processor.py:393-396)
     if (threadIdx.x < KT) fs_w[threadIdx.x] = 1.f;
+  }
+  if (EXP16) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + C::OFF_ONES);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) ones[i] = 0x3C003C00u;  // fp16 1.0 pairs
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -177,6 +186,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               const uint64_t db = umma_desc_sw128(smem_base + C::OFF_V + (st * NDCH + c) * C::KV_TILE + kk * 2048,
                                                   C::KV_TILE, 1024);
               mma_f16_ts(tmem + C::O_COL + 64 * c, tmem + kk * 8, db, IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
+            }
+            if (EXP16) {  // L[128 x 16] += P[128 x 16 keys] * ones: the softmax denominator on the tensor pipe
+              constexpr uint32_t IDESC_L = umma_idesc_f16(128, 16, 0, 1);
+              const uint64_t dl = umma_desc_sw128(smem_base + C::OFF_ONES, 2048, 1024);
+              mma_f16_ts(tmem + C::L_COL, tmem + kk * 8, dl, IDESC_L, (j > 0 || kk > 0) ? 1u : 0u);
             }
           }
           tc_commit(&kv_empty[st]);
@@ -355,10 +369,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                 tmem_st32(tlane + C::O_COL + 32 * c, o);
               }
+              if (EXP16) {
+                uint32_t o[16];
+                tmem_ld16(tlane + C::L_COL, o);
+                tmem_wait_ld_regs16(o);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st16(tlane + C::L_COL, o);
+              }
             }
           }
           float rowsum = 0.f;
-          {
+          if constexpr (EXP16) {
+            // packed-fp16 exponentials (2 per MUFU op); the row sum is accumulated by the L MMA, not here
+            uint32_t buf[2][32];
+            tmem_ld32(tlane, buf[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              tmem_wait_ld_regs32(buf[c & 1]);
+              if (c + 1 < 4) tmem_ld32(tlane + 32 * (c + 1), buf[(c + 1) & 1]);
+              uint32_t pk[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float x0 = fmaf(__uint_as_float(buf[c & 1][2 * i]), p.scale_log2, -m_ref);
+                float x1 = fmaf(__uint_as_float(buf[c & 1][2 * i + 1]), p.scale_log2, -m_ref);
+                if (valid < 32 * (c + 1)) {
+                  if (32 * c + 2 * i >= valid) x0 = -INFINITY;
+                  if (32 * c + 2 * i + 1 >= valid) x1 = -INFINITY;
+                }
+                pk[i] = ex2_f16x2(pack_half2(x0, x1));
+              }
+              tmem_st16(tlane + 16 * c, pk);
+            }
+          } else {
             uint32_t buf[2][32];
             tmem_ld32(tlane, buf[0]);
 #pragma unroll
@@ -398,6 +441,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // ---- epilogue for this head
       mbar_wait(o_full, hit & 1);
       tc_fence_after();
+      if (EXP16) {
+        uint32_t lv[16];
+        tmem_ld16(tlane + C::L_COL, lv);
+        tmem_wait_ld_regs16(lv);
+        l = __uint_as_float(lv[0]);
+      }
       const float inv_l = (KT == 80) ? 1.f : 1.f / l;
       if (threadIdx.x == 0) tma_store_wait_read();  // previous head's store has drained the staging tile
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
@@ -448,11 +497,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int KT, int NDCH, bool CAPTURE>
+template <int KT, int NDCH, bool CAPTURE, bool EXP16 = false>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                   const AttnParams& p, dim3 grid, cudaStream_t stream) {
-  using C = AttnCfg<KT, NDCH, CAPTURE>;
-  auto kern = attn_fwd_kernel<KT, NDCH, CAPTURE>;
+  using C = AttnCfg<KT, NDCH, CAPTURE, EXP16>;
+  auto kern = attn_fwd_kernel<KT, NDCH, CAPTURE, EXP16>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
@@ -468,6 +517,8 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 using namespace rtti;
 
 // A/B switch for profiling: RTTI_ATTN_KT64=1 selects the 64-key-tile / 3-CTA-per-SM kernel for head_dim <= 64.
+// RTTI_ATTN_EXP32=1 keeps fp32 exponentials in the head_dim<=64 self-attention kernel (default: packed fp16).
+static const bool g_exp16 = [] { const char* e = getenv("RTTI_ATTN_EXP32"); return !(e && e[0] == '1'); }();
 static const bool g_use_kt64 = [] { const char* e = getenv("RTTI_ATTN_KT64"); return e && e[0] == '1'; }();
 
 extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads,
@@ -540,6 +591,7 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
     RTTI_LAUNCH(80, 3, false);
   }
   if (KT == 64) RTTI_LAUNCH(64, 1, false);
+  if (ndch == 1 && g_exp16) return launch<128, 1, false, true>(tq, tk, tv, to, p, grid, st);
   if (ndch == 1) RTTI_LAUNCH(128, 1, false);
   if (ndch == 2) RTTI_LAUNCH(128, 2, false);
   RTTI_LAUNCH(128, 3, false);

@@ -9,6 +9,7 @@
 //      the masked region sums + classifier-free guidance + Euler update of
 //      models/region_diffusion_sdxl.py:810-845 — replicated on every rank, bit-identical results,
 //      so no broadcast of the latents is needed.
+// A peer that never publishes makes the wait give up after ~4 s and raise the error word flags[1] (checked by the host).
 // Slot buffers are double-buffered by step parity, which makes re-use safe without a trailing barrier:
 // a rank overwrites parity p at step s+2 only after its step s+1 kernel saw every peer publish s+1,
 // and a peer publishes s+1 only after its step-s kernel (the last reader of parity p) has finished.
@@ -63,9 +64,16 @@ __global__ void __launch_bounds__(128) gather_blend_kernel(const GatherBlendPara
   }
   if (threadIdx.x < p.world && threadIdx.x != p.rank) {
     unsigned int v;
+    long long spins = 0;
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p.peer_flags[threadIdx.x]) : "memory");
-      if ((int)(v - p.step_id) < 0) __nanosleep(200);
+      if ((int)(v - p.step_id) < 0) {
+        __nanosleep(500);
+        if (++spins > 8000000LL) {  // ~4 s: a peer never published (crashed / diverged) — flag it, do not hang the GPU
+          p.peer_flags[p.rank][1] = 0xDEADu;
+          break;
+        }
+      }
     } while ((int)(v - p.step_id) < 0);
   }
   __syncthreads();

@@ -235,6 +235,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
 }
+// two fp16 exponentials per MUFU op (the softmax of head_dim-64 attention is MUFU-bound on B200)
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;\n" : "=r"(y) : "r"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

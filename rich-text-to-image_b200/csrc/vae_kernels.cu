@@ -57,14 +57,12 @@ __global__ void gn32_partial_kernel(const float* __restrict__ x, const float* __
     }
   }
   const size_t base = ((size_t)b * hw) * c + vec * 4;
-  for (int r = r0 + rl; r < r1; r += rowlanes) {
-    const float4 xv = *reinterpret_cast<const float4*>(x + base + (size_t)r * c);
+  auto accumulate = [&](const float4& xv, const float4& dv) {
     const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
     if (MODE == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) { a[i] += xs[i]; q[i] += xs[i] * xs[i]; }
     } else {
-      const float4 dv = *reinterpret_cast<const float4*>(dz + base + (size_t)r * c);
       const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -79,6 +77,23 @@ __global__ void gn32_partial_kernel(const float* __restrict__ x, const float* __
         a[i] += t; q[i] += t * xh;
       }
     }
+  };
+  int r = r0 + rl;
+  for (; r + 3 * rowlanes < r1; r += 4 * rowlanes) {  // 4 (x2 in backward) independent 128-bit loads in flight
+    float4 xv[4], dv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      xv[u] = *reinterpret_cast<const float4*>(x + base + (size_t)(r + u * rowlanes) * c);
+      if (MODE == 1) dv[u] = *reinterpret_cast<const float4*>(dz + base + (size_t)(r + u * rowlanes) * c);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) accumulate(xv[u], dv[u]);
+  }
+  for (; r < r1; r += rowlanes) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + base + (size_t)r * c);
+    float4 dv = xv;
+    if (MODE == 1) dv = *reinterpret_cast<const float4*>(dz + base + (size_t)r * c);
+    accumulate(xv, dv);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -153,8 +168,7 @@ __global__ void gn32_apply_kernel(const float* __restrict__ x, const float* __re
   }
   const int r0 = chunk * rows_per_chunk, r1 = min(hw, r0 + rows_per_chunk);
   const size_t base = ((size_t)b * hw) * c + vec * 4;
-  for (int r = r0 + rl; r < r1; r += rowlanes) {
-    const float4 xv = *reinterpret_cast<const float4*>(x + base + (size_t)r * c);
+  auto apply = [&](const float4& xv, const float4& dv) -> float4 {
     const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
     float o[4];
     if (MODE == 0) {
@@ -164,7 +178,6 @@ __global__ void gn32_apply_kernel(const float* __restrict__ x, const float* __re
         o[i] = silu ? y * sigmoidf_(y) : y;
       }
     } else {
-      const float4 dv = *reinterpret_cast<const float4*>(dz + base + (size_t)r * c);
       const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -178,7 +191,25 @@ __global__ void gn32_apply_kernel(const float* __restrict__ x, const float* __re
         o[i] = rs[i] * (dy * ga[i] - c1[i] - xh * c2[i]);
       }
     }
-    *reinterpret_cast<float4*>(out + base + (size_t)r * c) = make_float4(o[0], o[1], o[2], o[3]);
+    return make_float4(o[0], o[1], o[2], o[3]);
+  };
+  int r = r0 + rl;
+  for (; r + 3 * rowlanes < r1; r += 4 * rowlanes) {
+    float4 xv[4], dv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      xv[u] = *reinterpret_cast<const float4*>(x + base + (size_t)(r + u * rowlanes) * c);
+      if (MODE == 1) dv[u] = *reinterpret_cast<const float4*>(dz + base + (size_t)(r + u * rowlanes) * c);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<float4*>(out + base + (size_t)(r + u * rowlanes) * c) = apply(xv[u], dv[u]);
+  }
+  for (; r < r1; r += rowlanes) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + base + (size_t)r * c);
+    float4 dv = xv;
+    if (MODE == 1) dv = *reinterpret_cast<const float4*>(dz + base + (size_t)r * c);
+    *reinterpret_cast<float4*>(out + base + (size_t)r * c) = apply(xv, dv);
   }
 }
 

@@ -358,4 +358,6 @@ class RegionDiffusionXL:
             self.rich_text_step(st, i)
             if callback is not None and i % callback_steps == 0:
                 callback(i, t, st.latents)
+        for ex in self._exchanges.values():
+            ex.check()
         return st.latents

@@ -166,6 +166,12 @@ class PeerExchange:
                 self.slots[par, self.slot_of_pass[p]].copy_(eps_local[k].reshape(-1))
         return self.step_id
 
+    def check(self):
+        """Raise if a fused exchange timed out waiting for a peer (error word set by the kernel)."""
+        err = int(self.buf[4:8].view(torch.int32).item())
+        if err != 0:
+            raise RuntimeError("rtti_gather_blend_step: timed out waiting for a peer rank's noise predictions")
+
     def slot_owner(self, owner):
         out = [0] * self.n_slots
         for p, s in enumerate(self.slot_of_pass):

@@ -324,3 +324,58 @@ def test_region_parallel_two_gpus_matches_reference_golden():
                        capture_output=True, text=True, timeout=900)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "MULTIGPU_CHECK PASS" in r.stdout
+
+
+def test_full_size_sd15_and_sdxl_runs_properties():
+    """BASELINE.json full sizes (SD1.5 512^2 / SDXL 1024^2, random weights): size-independent properties —
+    finite latents, token maps are probability rows (captured 32x32 self maps sum to (#captured calls) per row;
+    SD1.5's are overwritten -> 1), masks built from them sum to one per pixel, blend of identical passes is a no-op."""
+    from rtti_b200.attention_utils import get_token_maps
+    from rtti_b200.region_diffusion import RegionDiffusion
+    from rtti_b200.region_diffusion_sdxl import RegionDiffusionXL
+    g = torch.Generator().manual_seed(0)
+    # ---- SD1.5, 512x512, 3 regions (configs[1] shape), 12-step plain pass + 2 rich steps
+    sd = RegionDiffusion.from_synthetic(seed=0, device="cuda", with_vae=False)
+    ctx = torch.randn(4, 77, 768, generator=g).cuda()
+    sd.register_tokenmap_hooks()
+    lat = sd.produce_attn_maps(None, None, num_inference_steps=12, guidance_scale=8.5, latents=torch.randn(1, 4, 64, 64, generator=g),
+                               text_embeddings=torch.cat([ctx[:1], ctx[-1:]]), decode=False)
+    assert torch.isfinite(lat.float()).all()
+    for name, m in sd.selfattn_maps.items():
+        assert abs(float(m[0].sum(-1).mean()) - 1.0) < 2e-3, name          # overwritten: one call's rows
+    for name, m in sd.crossattn_maps.items():
+        assert abs(float(m[0].sum(-1).mean()) - 3.0) < 6e-3, name          # calls 11, 12, 13 accumulated
+    masks = get_token_maps(sd.selfattn_maps, sd.crossattn_maps, sd.n_maps, None, 64, 64,
+                           [torch.LongTensor([2]), torch.LongTensor([5, 6])], seed=3, num_segments=5)
+    total = torch.stack(masks).sum(0)
+    assert len(masks) == 3 and masks[0].shape == (1, 4, 64, 64) and (total - 1).abs().max().item() < 1e-4
+    sd.remove_tokenmap_hooks()
+    sd.masks = masks
+    out = sd.produce_latents(ctx, num_inference_steps=2, guidance_scale=8.5, latents=torch.randn(1, 4, 64, 64, generator=g),
+                             inject_selfattn=0.3, inject_background=0.5, text_format_dict={"word_pos": torch.LongTensor([3]),
+                                                                                          "font_size": torch.FloatTensor([2.0])})
+    assert torch.isfinite(out.float()).all()
+    del sd
+    torch.cuda.empty_cache()
+    # ---- SDXL, 1024x1024, 5 regions: 2 rich steps with everything on except the (weight-less) colour guidance
+    xl = RegionDiffusionXL.from_synthetic(seed=0, device="cuda", with_vae=False)
+    ctx = torch.randn(6, 77, 2048, generator=g).cuda()
+    te = torch.randn(6, 1280, generator=g).cuda()
+    logits = torch.randn(5, 1, 128, 128, generator=g)
+    m = torch.softmax(logits, 0)
+    xl.masks = [m[i:i + 1].repeat(1, 4, 1, 1).cuda() for i in range(5)]
+    out = xl.sample(num_inference_steps=3, guidance_scale=8.5, latents=torch.randn(1, 4, 128, 128, generator=g), prompt_embeds=ctx[1:],
+                    negative_prompt_embeds=ctx[:1], pooled_prompt_embeds=te[1:], negative_pooled_prompt_embeds=te[:1],
+                    output_type="latent", run_rich_text=True, inject_selfattn=0.5, inject_background=0.5,
+                    text_format_dict={"word_pos": torch.LongTensor([3]), "font_size": torch.FloatTensor([2.0])}).images
+    assert out.shape == (1, 4, 128, 128) and torch.isfinite(out.float()).all()
+    # graph replay and eager execution of the same step agree
+    xl.use_cuda_graphs = False
+    out2 = xl.sample(num_inference_steps=3, guidance_scale=8.5, latents=torch.randn(1, 4, 128, 128, generator=torch.Generator().manual_seed(5)),
+                     prompt_embeds=ctx[1:], negative_prompt_embeds=ctx[:1], pooled_prompt_embeds=te[1:],
+                     negative_pooled_prompt_embeds=te[:1], output_type="latent", run_rich_text=True, inject_selfattn=0.5).images
+    xl.use_cuda_graphs = True
+    out3 = xl.sample(num_inference_steps=3, guidance_scale=8.5, latents=torch.randn(1, 4, 128, 128, generator=torch.Generator().manual_seed(5)),
+                     prompt_embeds=ctx[1:], negative_prompt_embeds=ctx[:1], pooled_prompt_embeds=te[1:],
+                     negative_pooled_prompt_embeds=te[:1], output_type="latent", run_rich_text=True, inject_selfattn=0.5).images
+    assert torch.equal(out2, out3)
