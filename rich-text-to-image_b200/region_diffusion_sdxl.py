@@ -306,12 +306,15 @@ class RegionDiffusionXL:
         sigma = self.scheduler.sigma(t)
         scale = 1.0 / math.sqrt(sigma * sigma + 1.0)                                    # :784
         local = plan.local_passes(feat_inject_step)
-        x = torch.cat([(st.latents_ref if passes[p]["ref"] else st.latents) for p in local]) * scale
         pe = self.profile_events
         if pe is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
-        eps_local = self._unet_pass(st, x, t, local, feat_inject_step)
+        if local:
+            x = torch.cat([(st.latents_ref if passes[p]["ref"] else st.latents) for p in local]) * scale
+            eps_local = self._unet_pass(st, x, t, local, feat_inject_step)
+        else:   # more ranks than passes on this step: this rank only takes part in the exchange
+            eps_local = st.latents.new_empty((0,) + tuple(st.latents.shape[1:]))
         if pe is not None:
             ev[1].record()
         dt = self.scheduler.dt(t)

@@ -141,11 +141,6 @@ class PeerExchange:
             k = p["kind"]
             self.slot_of_pass.append({"A": 0, "B": n_regions, "C": n_regions + 1, "D": n_regions + 2}.get(k, 1 + p.get("region", 0)))
         nbytes = self.HEADER + 2 * self.n_slots * n * 2
-        if hasattr(symm, "enable_symm_mem_for_group"):
-            try:
-                symm.enable_symm_mem_for_group(self.group.group_name)
-            except Exception:
-                pass
         self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
         self.handle = symm.rendezvous(self.buf, self.group.group_name)
         self.buf.zero_()
