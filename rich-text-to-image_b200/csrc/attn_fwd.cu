@@ -517,8 +517,12 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 using namespace rtti;
 
 // A/B switch for profiling: RTTI_ATTN_KT64=1 selects the 64-key-tile / 3-CTA-per-SM kernel for head_dim <= 64.
-// RTTI_ATTN_EXP32=1 keeps fp32 exponentials in the head_dim<=64 self-attention kernel (default: packed fp16).
-static const bool g_exp16 = [] { const char* e = getenv("RTTI_ATTN_EXP32"); return !(e && e[0] == '1'); }();
+// RTTI_ATTN_EXP16=1 selects packed-fp16 exponentials + tensor-core row sums in the head_dim<=64 self-attention
+// kernel. Measured 21 % SLOWER than fp32 exponentials on B200 (profiles/r01_kernels_v3_*.jsonl): sm_100 executes
+// ex2.approx.f16x2 as two MUFU.EX2.F16 ops (the doubled SFU rate is an sm_103 feature), so it is off by default.
+static const bool g_exp16 = [] { const char* e = getenv("RTTI_ATTN_EXP16"); return e && e[0] == '1'; }();
+// RTTI_ATTN_V1=1 keeps the sequential 2-CTA/SM kernel of this file for head_dim <= 64 self-attention.
+static const bool g_v2 = [] { const char* e = getenv("RTTI_ATTN_V1"); return !(e && e[0] == '1'); }();
 static const bool g_use_kt64 = [] { const char* e = getenv("RTTI_ATTN_KT64"); return e && e[0] == '1'; }();
 
 extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads,
@@ -591,6 +595,8 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
     RTTI_LAUNCH(80, 3, false);
   }
   if (KT == 64) RTTI_LAUNCH(64, 1, false);
+  if (ndch == 1 && g_v2 && !g_exp16)   // software-pipelined kernel (attn_self_v2.cu): 1 CTA/SM, MMAs hidden behind exps
+    return launch_attn_self_v2(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.qk_src, lse, st);
   if (ndch == 1 && g_exp16) return launch<128, 1, false, true>(tq, tk, tv, to, p, grid, st);
   if (ndch == 1) RTTI_LAUNCH(128, 1, false);
   if (ndch == 2) RTTI_LAUNCH(128, 2, false);

@@ -344,7 +344,9 @@ class RegionDiffusionXL:
         if pe is not None:
             ev[2].record()
         if st.use_guidance and float(t) < st.tfd["guidance_start_step"]:                                  # :849
+            torch.cuda.nvtx.range_push("guidance")
             st.latents = self._color_guidance(st.latents, st.noise_pred, t, st.tfd)
+            torch.cuda.nvtx.range_pop()
         if i == int(st.inject_background * st.n_t) and st.inject_background > 0:                          # :870-872
             st.latents = ops.bg_inject_blend(st.latents.contiguous(), st.latents_ref.contiguous(), st.masks[-1].contiguous())
         if pe is not None:

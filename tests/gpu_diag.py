@@ -191,9 +191,13 @@ CASES = {
     "d8": lambda: attn_case(2, 4, 8, 64, 77),
     "cross_xl64": lambda: attn_case(8, 10, 64, 4096, 77),
     "self_xl32": lambda: attn_case(8, 20, 64, 1024, 1024, fused_qkv=True),
-    # fp32-exponential variant of the head_dim<=64 kernel (default is packed fp16): run with RTTI_ATTN_EXP32=1
-    "exp32:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    "exp32:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
+    # packed-fp16-exponential variant of the head_dim<=64 kernel (experiment, off by default): RTTI_ATTN_EXP16=1
+    "exp16:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    "exp16:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
+    # the sequential 2-CTA/SM kernel (v1) for head_dim <= 64: RTTI_ATTN_V1=1
+    "v1:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    "v1:self_inject": lambda: attn_case(4, 2, 64, 256, 256, qk_src=[0, 1, 1, 1]),
+    "v1:d40": lambda: attn_case(2, 8, 40, 256, 256),
     # 64-key-tile / 3 CTAs per SM experiment: RTTI_ATTN_KT64=1
     "kt64:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
 }
@@ -206,10 +210,12 @@ if __name__ == "__main__":
     for name in CASES:
         try:
             env = dict(os.environ)
-            if name.startswith("exp32:"):
-                env["RTTI_ATTN_EXP32"] = "1"
+            if name.startswith("exp16:"):
+                env["RTTI_ATTN_EXP16"] = "1"; env["RTTI_ATTN_V1"] = "1"
             if name.startswith("kt64:"):
-                env["RTTI_ATTN_KT64"] = "1"
+                env["RTTI_ATTN_KT64"] = "1"; env["RTTI_ATTN_V1"] = "1"
+            if name.startswith("v1:"):
+                env["RTTI_ATTN_V1"] = "1"
             r = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=120, capture_output=True, text=True, env=env)
             out = (r.stdout + r.stderr).strip()
             status = "ok" if r.returncode == 0 else f"rc={r.returncode}"

@@ -16,10 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize("case", list(gpu_diag.CASES))
 def test_kernel_case(case):
     env = dict(os.environ)
-    if case.startswith("exp32:"):
-        env["RTTI_ATTN_EXP32"] = "1"
+    if case.startswith("exp16:"):
+        env["RTTI_ATTN_EXP16"] = "1"; env["RTTI_ATTN_V1"] = "1"
     if case.startswith("kt64:"):
-        env["RTTI_ATTN_KT64"] = "1"
+        env["RTTI_ATTN_KT64"] = "1"; env["RTTI_ATTN_V1"] = "1"
+    if case.startswith("v1:"):
+        env["RTTI_ATTN_V1"] = "1"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gpu_diag.py"), case], capture_output=True, text=True,
                        timeout=300, env=env)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
