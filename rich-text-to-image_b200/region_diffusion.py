@@ -23,6 +23,7 @@ from .vae import AutoencoderKLDecoder, VAEConfig
 class RegionDiffusion:
     def __init__(self, device="cuda", unet=None, vae=None, text_encoder=None, load_path="runwayml/stable-diffusion-v1-5"):
         self.device = torch.device(device)
+        torch.backends.cudnn.benchmark = True   # static shapes: let cuDNN pick its fastest conv algorithm once
         self.num_train_timesteps = 1000
         if unet is None:
             from .loading import load_sd15_components

@@ -39,6 +39,7 @@ class RegionDiffusionXL:
         directory as `load_path` (models/region_diffusion_sdxl.py:87-137 downloads from the hub; there is
         no network here, so only local paths are supported)."""
         self.device = torch.device(device)
+        torch.backends.cudnn.benchmark = True   # static shapes: let cuDNN pick its fastest conv algorithm once
         self.device_type = device
         if unet is None:
             from .loading import load_sdxl_components
