@@ -132,12 +132,19 @@ int rtti_predict_x0(const void* x_t, const void* eps, float alpha, void* x0, lon
  * models/region_diffusion.py:157-165). x, y, dz, dx: [batch, hw, c] fp32; gamma/beta [c] fp32;
  * mean_rstd [batch, groups, 2] fp32 (written by fwd, read by bwd); workspace fp32
  * [rtti_gn32_workspace_elems(...)]. dx = d loss / d x given dz = d loss / d (silu?(GN(x))).
+ * chan_bias: optional fp32 [c] added to x first (the bias of the convolution that produced x, folded in); NULL to skip.
  */
 long long rtti_gn32_workspace_elems(int batch, int hw, int c, int groups);
-int rtti_gn32_silu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd,
-                       float* workspace, int batch, int hw, int c, int groups, float eps, int apply_silu, void* stream);
-int rtti_gn32_silu_bwd(const float* x, const float* dz, const float* gamma, const float* beta, const float* mean_rstd,
-                       float* dx, float* workspace, int batch, int hw, int c, int groups, int apply_silu, void* stream);
+int rtti_gn32_silu_fwd(const float* x, const float* chan_bias, const float* gamma, const float* beta, float* y,
+                       float* mean_rstd, float* workspace, int batch, int hw, int c, int groups, float eps,
+                       int apply_silu, void* stream);
+int rtti_gn32_silu_bwd(const float* x, const float* chan_bias, const float* dz, const float* gamma, const float* beta,
+                       const float* mean_rstd, float* dx, float* workspace, int batch, int hw, int c, int groups,
+                       int apply_silu, void* stream);
+/* out[rows, c] = a + b + bias[c] (fp32): the residual add of a VAE resnet block fused with the bias of the
+ * convolution that produced b; bias may be NULL. */
+int rtti_add_bias_f32(const float* a, const float* b, const float* bias, float* out, long long rows, int c,
+                      void* stream);
 
 /* Multi-GPU region parallelism (new relative to the single-GPU reference loop,
  * models/region_diffusion_sdxl.py:779-845): fused all-gather + region blend + CFG + Euler update over NVLink

@@ -5,15 +5,13 @@
 // tensor pipe; at head_dim 64 that leaves the kernel ~2x off its real bound, which is the MUFU (exp2) pipe:
 // 128x128 exponentials per tile = 1024 cycles on 16 lanes/SM vs 512 cycles of MMA. v2 hides the MMAs
 // completely behind the exponentials inside ONE CTA per SM:
-//   * S is triple-buffered in TMEM (S0..S2 at columns [0,384), O at [384,448)): the MMA warp issues QK^T two
-//     tiles ahead of the softmax, then PV of tile j as soon as P_j is written;
+//   * S is double-buffered in TMEM (S0 [0,128), S1 [128,256), O [256,320)): the MMA warp issues QK^T of tile
+//     j+1 before the softmax of tile j has finished, then PV of tile j as soon as P_j is written;
 //   * 8 softmax warps (2 threads per query row, 64 keys each) keep 2 warps per SM sub-partition so the MUFU
 //     pipe stays busy across TMEM-load and barrier latencies; the row max is combined through shared memory;
 //   * P_j overwrites its own S buffer as packed fp16 and feeds the PV MMA from TMEM (TS operand);
 //   * the lazy O rescale (rare) waits for PV_{j-1} on its own barrier, because QK^T_{j} no longer implies it.
-//   * each softmax thread issues the TMEM load of S_{j+1} before the exponentials of tile j and computes its row
-//     max behind them (software pipelining), so the MUFU pipe idles only for the P store and one named barrier;
-// Warps: 0-7 softmax/epilogue, 8 TMA producer, 9 MMA issuer + TMEM owner. 4-stage K/V ring.
+// Warps: 0-7 softmax/epilogue, 8 TMA producer, 9 MMA issuer + TMEM owner. 3-stage K/V ring.
 #include "ptx.cuh"
 #include "rtti_internal.h"
 
@@ -28,7 +26,7 @@ struct AttnV2Params {
 
 namespace v2 {
 constexpr int KT = 128;
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 3;
 constexpr int Q_TILE = 128 * 128;   // bytes
 constexpr int KV_TILE = KT * 128;
 constexpr int OFF_Q = 0;
@@ -38,7 +36,7 @@ constexpr int OFF_O = OFF_V + NSTAGE * KV_TILE;
 constexpr int OFF_BAR = OFF_O + Q_TILE;
 constexpr int OFF_RED = OFF_BAR + 256;              // float red_max[2 parities][2 halves][128] + red_l[2][128]
 constexpr int SMEM_BYTES = OFF_RED + (2 * 2 * 128 + 2 * 128) * 4 + 1024;
-constexpr uint32_t O_COL = 384;   // S0 [0,128), S1 [128,256), S2 [256,384), O [384,448)
+constexpr uint32_t S_COL0 = 0, S_COL1 = 128, O_COL = 256;
 constexpr int THREADS = 320;
 }  // namespace v2
 
@@ -51,14 +49,14 @@ attn_self_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // [4]
-  uint64_t* v_full = bars + 5;        // [4]
-  uint64_t* kv_empty = bars + 9;      // [4]
-  uint64_t* s_full = bars + 13;       // [3]
-  uint64_t* p_full = bars + 16;       // [3]
-  uint64_t* pv_done = bars + 19;      // 1, one phase per key tile
-  uint64_t* o_full = bars + 20;       // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* k_full = bars + 1;        // [3]
+  uint64_t* v_full = bars + 4;        // [3]
+  uint64_t* kv_empty = bars + 7;      // [3]
+  uint64_t* s_full = bars + 10;       // [2]
+  uint64_t* p_full = bars + 12;       // [2]
+  uint64_t* pv_done = bars + 14;      // 1, one phase per key tile
+  uint64_t* o_full = bars + 15;       // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   float* red_max = reinterpret_cast<float*>(smem + OFF_RED);   // [parity][half][row]
   float* red_l = red_max + 2 * 2 * 128;                        // [half][row]
 
@@ -73,7 +71,7 @@ attn_self_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
     mbar_init(q_full, 1);
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); }
     mbar_init(pv_done, 1); mbar_init(o_full, 1);
     mbar_fence_init();
   }
@@ -107,28 +105,26 @@ attn_self_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int st = j % NSTAGE;
         mbar_wait(&k_full[st], (j / NSTAGE) & 1);
         tc_fence_after();
-        const uint32_t s_col = 128u * (j % 3);
+        const uint32_t s_col = (j & 1) ? S_COL1 : S_COL0;
         for (int kk = 0; kk < p.ksteps_qk; ++kk) {
           const uint64_t da = umma_desc_sw128(smem_base + OFF_Q + kk * 32, 0, 1024);
           const uint64_t db = umma_desc_sw128(smem_base + OFF_K + st * KV_TILE + kk * 32, 0, 1024);
           mma_f16_ss(tmem + s_col, da, db, IDESC_QK, kk > 0);
         }
-        tc_commit(&s_full[j % 3]);
+        tc_commit(&s_full[j & 1]);
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
       issue_qk(0);
-      if (nt > 1) issue_qk(1);
       for (int j = 0; j < nt; ++j) {
-        // two tiles of look-ahead: S[(j+2)%3] held P_{j-1}; PV_{j-1} was issued in the previous iteration and the
-        // tensor pipe executes in issue order, so QK^T_{j+2} cannot overtake it
-        if (j + 2 < nt) issue_qk(j + 2);
+        // S[(j+1)&1] held P_{j-1}; PV_{j-1} was issued in the previous iteration and the pipe is in-order
+        if (j + 1 < nt) issue_qk(j + 1);
         const int st = j % NSTAGE;
-        mbar_wait(&p_full[j % 3], (j / 3) & 1);
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
         mbar_wait(&v_full[st], (j / NSTAGE) & 1);
         tc_fence_after();
-        const uint32_t p_col = 128u * (j % 3);
+        const uint32_t p_col = (j & 1) ? S_COL1 : S_COL0;
 #pragma unroll
         for (int kk = 0; kk < KT / 16; ++kk) {
           const uint64_t db = umma_desc_sw128(smem_base + OFF_V + st * KV_TILE + kk * 2048, KV_TILE, 1024);
@@ -146,42 +142,29 @@ attn_self_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t tlane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const bool row_ok = (q0 + row) < p.n_q;
     float m_ref = -INFINITY, l = 0.f;
-    // Software pipeline inside each softmax thread: S is triple-buffered, so S_{j+1} is complete before the
-    // exponentials of tile j start. Its TMEM load is ISSUED before the exp burst and waited for after it, the
-    // row max of tile j+1 is computed and exchanged behind it: between two MUFU bursts only the max, the P store
-    // and one named barrier remain.
-    auto issue_load = [&](int j, float* sv) {
-      const uint32_t s_col = 128u * (j % 3);
-      mbar_wait(&s_full[j % 3], (j / 3) & 1);
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t s_col = ((j & 1) ? S_COL1 : S_COL0);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      tmem_ld32(tlane + s_col + 64 * half, reinterpret_cast<uint32_t*>(sv));
-      tmem_ld32(tlane + s_col + 64 * half + 32, reinterpret_cast<uint32_t*>(sv) + 32);
-    };
-    auto finish_max = [&](int j, float* sv) -> float {
-      tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(sv));
-      tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(sv) + 32);
+      float s[64];
+      tmem_ld32(tlane + s_col + 64 * half, reinterpret_cast<uint32_t*>(s));
+      tmem_ld32(tlane + s_col + 64 * half + 32, reinterpret_cast<uint32_t*>(s) + 32);
+      tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s));
+      tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s) + 32);
       const int valid = p.n_k - j * KT - 64 * half;   // valid keys among my 64
       if (valid < 64) {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
-          if (i >= valid) sv[i] = -INFINITY;
+          if (i >= valid) s[i] = -INFINITY;
       }
-      float mx = sv[0];
+      float mx = s[0];
 #pragma unroll
-      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, sv[i]);
-      return mx;
-    };
-    auto exchange_max = [&](int j, float mx) -> float {
+      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
       float* rm = red_max + (j & 1) * 256;
       rm[half * 128 + row] = mx;
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
-      return fmaxf(mx, rm[(half ^ 1) * 128 + row]) * p.scale_log2;
-    };
-    float s[64];
-    issue_load(0, s);
-    float mxs = exchange_max(0, finish_max(0, s));
-    for (int j = 0; j < nt; ++j) {
-      const uint32_t s_col = 128u * (j % 3);
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");   // also: every thread has finished reading S_j
+      mx = fmaxf(mx, rm[(half ^ 1) * 128 + row]);
+      const float mxs = mx * p.scale_log2;
       if (j == 0) {
         m_ref = mxs;
       } else {
@@ -200,8 +183,6 @@ attn_self_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tmem_st32(tlane + O_COL + 32 * half, o);
         }
       }
-      float sn[64];
-      if (j + 1 < nt) issue_load(j + 1, sn);             // asynchronous: lands while the MUFU burst below runs
       float rowsum = 0.f;
       uint32_t pk[32];
 #pragma unroll
@@ -212,19 +193,10 @@ attn_self_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         pk[i] = pack_half2(e0, e1);
       }
       l += rowsum;
-      // every thread of the row group read S_j long ago (before the exchange of the previous iteration), so P_j may
-      // overwrite it: packed P_j, keys 64*half.. -> columns 32*half..
-      tmem_st32(tlane + s_col + 32 * half, pk);
-      float mx_next = 0.f;
-      if (j + 1 < nt) mx_next = finish_max(j + 1, sn);
+      tmem_st32(tlane + s_col + 32 * half, pk);          // packed P_j over S_j: keys 64*half.. -> columns 32*half..
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[j % 3]);
-      if (j + 1 < nt) {
-        mxs = exchange_max(j + 1, mx_next);
-#pragma unroll
-        for (int i = 0; i < 64; ++i) s[i] = sn[i];
-      }
+      mbar_arrive(&p_full[j & 1]);
     }
     // ---- epilogue
     red_l[half * 128 + row] = l;

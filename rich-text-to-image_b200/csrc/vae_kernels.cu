@@ -33,7 +33,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 
 // MODE 0: (sum x, sum x^2).  MODE 1: backward sums (sum dy*gamma, sum dy*gamma*xhat).
 template <int MODE>
-__global__ void gn32_partial_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+__global__ void gn32_partial_kernel(const float* __restrict__ x, const float* __restrict__ cbias,
+                                    const float* __restrict__ dz,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ mean_rstd, float* __restrict__ ws, int hw, int c,
                                     int groups, int nvec, int rowlanes, int rows_per_chunk, int chunks, int silu) {
@@ -44,6 +45,8 @@ __global__ void gn32_partial_kernel(const float* __restrict__ x, const float* __
   const int r0 = chunk * rows_per_chunk, r1 = min(hw, r0 + rows_per_chunk);
   float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   float ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f}, mu[4], rs[4];
+  float cb[4] = {0.f, 0.f, 0.f, 0.f};   // per-channel bias of the producing convolution, folded in (x := x + cb)
+  if (cbias) { const float4 c4 = *reinterpret_cast<const float4*>(cbias + vec * 4); cb[0] = c4.x; cb[1] = c4.y; cb[2] = c4.z; cb[3] = c4.w; }
   if (MODE == 1) {
     const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
     const float4 b4 = *reinterpret_cast<const float4*>(beta + vec * 4);
@@ -58,7 +61,7 @@ __global__ void gn32_partial_kernel(const float* __restrict__ x, const float* __
   }
   const size_t base = ((size_t)b * hw) * c + vec * 4;
   auto accumulate = [&](const float4& xv, const float4& dv) {
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float xs[4] = {xv.x + cb[0], xv.y + cb[1], xv.z + cb[2], xv.w + cb[3]};
     if (MODE == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) { a[i] += xs[i]; q[i] += xs[i] * xs[i]; }
@@ -146,7 +149,8 @@ __global__ void gn32_finalize_kernel(const float* __restrict__ ws, float* __rest
 
 // MODE 0: y = silu?(xhat*gamma+beta).  MODE 1: dx = rstd*(dy*gamma - c1 - xhat*c2)
 template <int MODE>
-__global__ void gn32_apply_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+__global__ void gn32_apply_kernel(const float* __restrict__ x, const float* __restrict__ cbias,
+                                  const float* __restrict__ dz,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   const float* __restrict__ mean_rstd, const float* __restrict__ c12,
                                   float* __restrict__ out, int hw, int c, int groups, int nvec, int rowlanes,
@@ -155,6 +159,8 @@ __global__ void gn32_apply_kernel(const float* __restrict__ x, const float* __re
   const int vec = threadIdx.x % nvec, rl = threadIdx.x / nvec;
   const int cpg = c / groups;
   float ga[4], be[4], mu[4], rs[4], c1[4], c2[4];
+  float cb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (cbias) { const float4 c4 = *reinterpret_cast<const float4*>(cbias + vec * 4); cb[0] = c4.x; cb[1] = c4.y; cb[2] = c4.z; cb[3] = c4.w; }
   const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
   const float4 b4 = *reinterpret_cast<const float4*>(beta + vec * 4);
   ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w;
@@ -169,7 +175,7 @@ __global__ void gn32_apply_kernel(const float* __restrict__ x, const float* __re
   const int r0 = chunk * rows_per_chunk, r1 = min(hw, r0 + rows_per_chunk);
   const size_t base = ((size_t)b * hw) * c + vec * 4;
   auto apply = [&](const float4& xv, const float4& dv) -> float4 {
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float xs[4] = {xv.x + cb[0], xv.y + cb[1], xv.z + cb[2], xv.w + cb[3]};
     float o[4];
     if (MODE == 0) {
 #pragma unroll
@@ -231,7 +237,7 @@ extern "C" long long rtti_gn32_workspace_elems(int batch, int hw, int c, int gro
   return (long long)batch * p.chunks * groups * 2 + (long long)batch * groups * 2;
 }
 
-extern "C" int rtti_gn32_silu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd,
+extern "C" int rtti_gn32_silu_fwd(const float* x, const float* chan_bias, const float* gamma, const float* beta, float* y, float* mean_rstd,
                                   float* workspace, int batch, int hw, int c, int groups, float eps, int apply_silu,
                                   void* stream) {
   int rc = gn32_check(x, gamma, beta, y, batch, hw, c, groups);
@@ -242,16 +248,16 @@ extern "C" int rtti_gn32_silu_fwd(const float* x, const float* gamma, const floa
   if (smem > 48 * 1024) return RTTI_ERR_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(p.chunks, batch);
-  gn32_partial_kernel<0><<<grid, p.threads, smem, st>>>(x, nullptr, gamma, beta, nullptr, workspace, hw, c, groups,
+  gn32_partial_kernel<0><<<grid, p.threads, smem, st>>>(x, chan_bias, nullptr, gamma, beta, nullptr, workspace, hw, c, groups,
                                                         p.nvec, p.rowlanes, p.rows_per_chunk, p.chunks, 0);
   gn32_finalize_kernel<0><<<dim3((groups + 7) / 8, batch), 256, 0, st>>>(workspace, mean_rstd, groups, p.chunks,
                                                                          (float)hw * (float)(c / groups), eps);
-  gn32_apply_kernel<0><<<grid, p.threads, 0, st>>>(x, nullptr, gamma, beta, mean_rstd, nullptr, y, hw, c, groups,
+  gn32_apply_kernel<0><<<grid, p.threads, 0, st>>>(x, chan_bias, nullptr, gamma, beta, mean_rstd, nullptr, y, hw, c, groups,
                                                    p.nvec, p.rowlanes, p.rows_per_chunk, apply_silu);
   return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
 }
 
-extern "C" int rtti_gn32_silu_bwd(const float* x, const float* dz, const float* gamma, const float* beta,
+extern "C" int rtti_gn32_silu_bwd(const float* x, const float* chan_bias, const float* dz, const float* gamma, const float* beta,
                                   const float* mean_rstd, float* dx, float* workspace, int batch, int hw, int c,
                                   int groups, int apply_silu, void* stream) {
   int rc = gn32_check(x, gamma, beta, dx, batch, hw, c, groups);
@@ -263,11 +269,35 @@ extern "C" int rtti_gn32_silu_bwd(const float* x, const float* dz, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(p.chunks, batch);
   float* c12 = workspace + (size_t)batch * p.chunks * groups * 2;
-  gn32_partial_kernel<1><<<grid, p.threads, smem, st>>>(x, dz, gamma, beta, mean_rstd, workspace, hw, c, groups, p.nvec,
+  gn32_partial_kernel<1><<<grid, p.threads, smem, st>>>(x, chan_bias, dz, gamma, beta, mean_rstd, workspace, hw, c, groups, p.nvec,
                                                         p.rowlanes, p.rows_per_chunk, p.chunks, apply_silu);
   gn32_finalize_kernel<1><<<dim3((groups + 7) / 8, batch), 256, 0, st>>>(workspace, c12, groups, p.chunks,
                                                                          (float)hw * (float)(c / groups), 0.f);
-  gn32_apply_kernel<1><<<grid, p.threads, 0, st>>>(x, dz, gamma, beta, mean_rstd, c12, dx, hw, c, groups, p.nvec,
+  gn32_apply_kernel<1><<<grid, p.threads, 0, st>>>(x, chan_bias, dz, gamma, beta, mean_rstd, c12, dx, hw, c, groups, p.nvec,
                                                    p.rowlanes, p.rows_per_chunk, apply_silu);
+  return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
+}
+
+// out[r, c] = a[r, c] + b[r, c] + bias[c]   (residual add fused with the bias of the convolution that produced b)
+__global__ void add_bias_f32_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                    const float* __restrict__ bias, float* __restrict__ out, long long nvec, int cvec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = reinterpret_cast<const float4*>(a)[i];
+    const float4 y = reinterpret_cast<const float4*>(b)[i];
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) z = reinterpret_cast<const float4*>(bias)[i % cvec];
+    reinterpret_cast<float4*>(out)[i] = make_float4(x.x + y.x + z.x, x.y + y.y + z.y, x.z + y.z + z.z, x.w + y.w + z.w);
+  }
+}
+
+extern "C" int rtti_add_bias_f32(const float* a, const float* b, const float* bias, float* out, long long rows, int c,
+                                 void* stream) {
+  if (!a || !b || !out || rows < 1 || c < 4) return RTTI_ERR_ARG;
+  if (c % 4 != 0) return RTTI_ERR_SHAPE;
+  if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out | (uintptr_t)bias) & 15) return RTTI_ERR_ALIGN;
+  const long long nvec = rows * (c / 4);
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  add_bias_f32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a, b, bias, out, nvec, c / 4);
   return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
 }

@@ -278,7 +278,7 @@ def _gn32_workspace(x, groups):
     return ws
 
 
-def gn32_silu_fwd(x, gamma, beta, groups, eps, silu):
+def gn32_silu_fwd(x, gamma, beta, groups, eps, silu, chan_bias=None):
     """fp32 channels-last GroupNorm(+SiLU): x [B, HW, C] -> (y, mean_rstd [B, G, 2])  (rtti_gn32_silu_fwd)."""
     lib = _lib.load()
     _req(x, torch.float32, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
@@ -286,22 +286,34 @@ def gn32_silu_fwd(x, gamma, beta, groups, eps, silu):
     B, HW, C = x.shape
     y = torch.empty_like(x)
     stats = torch.empty(B, groups, 2, dtype=torch.float32, device=x.device)
-    rc = lib.rtti_gn32_silu_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), _ptr(_gn32_workspace(x, groups)),
+    rc = lib.rtti_gn32_silu_fwd(_ptr(x), _ptr(chan_bias), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), _ptr(_gn32_workspace(x, groups)),
                                 B, HW, C, groups, float(eps), 1 if silu else 0, _stream())
     _lib.check(rc, "rtti_gn32_silu_fwd")
     _count(3)
     return y, stats
 
 
-def gn32_silu_bwd(x, dz, gamma, beta, stats, groups, silu):
+def gn32_silu_bwd(x, dz, gamma, beta, stats, groups, silu, chan_bias=None):
     """Input gradient of gn32_silu_fwd (rtti_gn32_silu_bwd)."""
     lib = _lib.load()
     _req(x, torch.float32, "x"); _req(dz, torch.float32, "dz")
     assert x.is_contiguous() and dz.is_contiguous() and dz.shape == x.shape
     B, HW, C = x.shape
     dx = torch.empty_like(x)
-    rc = lib.rtti_gn32_silu_bwd(_ptr(x), _ptr(dz), _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(dx),
+    rc = lib.rtti_gn32_silu_bwd(_ptr(x), _ptr(chan_bias), _ptr(dz), _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(dx),
                                 _ptr(_gn32_workspace(x, groups)), B, HW, C, groups, 1 if silu else 0, _stream())
     _lib.check(rc, "rtti_gn32_silu_bwd")
     _count(3)
     return dx
+
+
+def add_bias_f32(a, b, bias=None):
+    """a + b + bias[c] for fp32 [.., C] tensors (rtti_add_bias_f32)."""
+    lib = _lib.load()
+    _req(a, torch.float32, "a"); _req(b, torch.float32, "b")
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    C = a.shape[-1]
+    out = torch.empty_like(a)
+    _lib.check(lib.rtti_add_bias_f32(_ptr(a), _ptr(b), _ptr(bias), _ptr(out), a.numel() // C, C, _stream()), "rtti_add_bias_f32")
+    _count(1)
+    return out

@@ -41,8 +41,10 @@ def _cl(y):
     return y.view(B, H * W, C), H, W
 
 
-def _conv_f(conv, x, H, W):
-    y = F.conv2d(_nchw(x, H, W), conv.weight, conv.bias, conv.stride, conv.padding)
+def _conv_f(conv, x, H, W, with_bias=True):
+    """with_bias=False: the caller folds conv.bias into the consumer (GroupNorm kernel / fused residual add) —
+    PyTorch otherwise adds the bias of a channels-last fp32 convolution in a separate broadcast pass."""
+    y = F.conv2d(_nchw(x, H, W), conv.weight, conv.bias if with_bias else None, conv.stride, conv.padding)
     return _cl(y)[0]
 
 
@@ -55,14 +57,14 @@ class DecoderFwdBwd:
         self._dummies = {}
 
     # ------------------------------------------------------------------ pieces
-    def _gn_f(self, norm, x, silu, tape):
-        y, stats = ops.gn32_silu_fwd(x, norm.weight, norm.bias, self.groups, norm.eps, silu)
-        tape.append(("gn", norm, x, stats, silu))
+    def _gn_f(self, norm, x, silu, tape, chan_bias=None):
+        y, stats = ops.gn32_silu_fwd(x, norm.weight, norm.bias, self.groups, norm.eps, silu, chan_bias=chan_bias)
+        tape.append(("gn", norm, x, stats, silu, chan_bias))
         return y
 
     def _gn_b(self, rec, g):
-        _, norm, x, stats, silu = rec
-        return ops.gn32_silu_bwd(x, g.contiguous(), norm.weight, norm.bias, stats, self.groups, silu)
+        _, norm, x, stats, silu, chan_bias = rec
+        return ops.gn32_silu_bwd(x, g.contiguous(), norm.weight, norm.bias, stats, self.groups, silu, chan_bias=chan_bias)
 
     def _dummy(self, shape, dev):
         k = (tuple(shape), str(dev))
@@ -78,12 +80,12 @@ class DecoderFwdBwd:
 
     def _resnet_f(self, r, x, H, W, tape):
         h = self._gn_f(r.norm1, x, True, tape)
-        h = _conv_f(r.conv1, h, H, W)
-        h = self._gn_f(r.norm2, h, True, tape)
-        h = _conv_f(r.conv2, h, H, W)
+        h = _conv_f(r.conv1, h, H, W, with_bias=False)
+        h = self._gn_f(r.norm2, h, True, tape, chan_bias=r.conv1.bias)   # conv1 bias folded into the norm
+        h = _conv_f(r.conv2, h, H, W, with_bias=False)
         sc = _conv_f(r.conv_shortcut, x, H, W) if r.conv_shortcut is not None else x
         tape.append(("res", r, H, W))
-        return sc + h
+        return ops.add_bias_f32(sc, h, r.conv2.bias)                      # residual + conv2 bias in one pass
 
     def _resnet_b(self, tape, g):
         _, r, H, W = tape.pop()
@@ -93,10 +95,8 @@ class DecoderFwdBwd:
         dh = self._conv_b(r.conv1, dh, cin, H, W)
         dx = self._gn_b(tape.pop(), dh)
         if r.conv_shortcut is not None:
-            dx = dx + self._conv_b(r.conv_shortcut, g, cin, H, W)
-        else:
-            dx = dx + g
-        return dx
+            return ops.add_bias_f32(dx, self._conv_b(r.conv_shortcut, g, cin, H, W))
+        return ops.add_bias_f32(dx, g.contiguous())
 
     def _attn_f(self, a, x, tape):
         """Single-head self-attention over all tokens (vae._MidAttention), probabilities materialised."""

@@ -310,6 +310,15 @@ def test_gn32_kernels_match_torch():
             dx = ops.gn32_silu_bwd(x.detach().contiguous(), dz, ga, be, stats, G, silu)
             _close(y.cpu(), ref.detach().cpu(), 1e-4, 1e-4, f"gn32 fwd C{C} silu={silu}")
             _close(dx.cpu(), gx.cpu(), 2e-4, 1e-3, f"gn32 bwd C{C} silu={silu}")
+            # folded per-channel bias: GN(x + b) evaluated on x with chan_bias=b
+            cb = torch.randn(C, device="cuda", generator=g)
+            xb = (x.detach() - cb).contiguous()
+            y2, st2 = ops.gn32_silu_fwd(xb, ga, be, G, 1e-6, silu, chan_bias=cb)
+            dx2 = ops.gn32_silu_bwd(xb, dz, ga, be, st2, G, silu, chan_bias=cb)
+            _close(y2.cpu(), ref.detach().cpu(), 2e-4, 1e-4, f"gn32 fwd+bias C{C} silu={silu}")
+            _close(dx2.cpu(), gx.cpu(), 4e-4, 1e-3, f"gn32 bwd+bias C{C} silu={silu}")
+        a, b2 = torch.randn(B, HW, C, device="cuda", generator=g), torch.randn(B, HW, C, device="cuda", generator=g)
+        assert torch.allclose(ops.add_bias_f32(a, b2, ga), a + b2 + ga, atol=1e-6)
 
 
 def test_region_parallel_two_gpus_matches_reference_golden():
