@@ -523,6 +523,8 @@ using namespace rtti;
 static const bool g_exp16 = [] { const char* e = getenv("RTTI_ATTN_EXP16"); return e && e[0] == '1'; }();
 // RTTI_ATTN_V1=1 keeps the sequential 2-CTA/SM kernel of this file for head_dim <= 64 self-attention.
 static const bool g_v2 = [] { const char* e = getenv("RTTI_ATTN_V1"); return !(e && e[0] == '1'); }();
+// RTTI_ATTN_V2=1 selects the 1-CTA/SM, 2-threads-per-row schedule (v2) instead of v3 for head_dim <= 64.
+static const bool g_v3 = [] { const char* e = getenv("RTTI_ATTN_V2"); return !(e && e[0] == '1'); }();
 static const bool g_use_kt64 = [] { const char* e = getenv("RTTI_ATTN_KT64"); return e && e[0] == '1'; }();
 
 extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads,
@@ -546,7 +548,8 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
   const int ndch = (head_dim + 63) / 64;
   // 77 text keys: one 80-key tile; otherwise 128-key tiles (2 CTAs/SM). The 64-key / 3-CTA variant measured
   // 15 % slower on B200 (profiles/r01_kernels_*.jsonl) and is kept behind RTTI_ATTN_KT64=1 for experiments.
-  const int KT = (n_k <= 80) ? 80 : ((ndch == 1 && g_use_kt64) ? 64 : 128);
+  const bool use_v3 = (n_k > 80 && ndch == 1 && g_v3 && !g_exp16 && !g_use_kt64 && g_v2);
+  const int KT = (n_k <= 80) ? 80 : ((ndch == 1 && (g_use_kt64 || use_v3)) ? 64 : 128);
   AttnParams p{};
   p.batch = batch; p.heads = heads; p.head_dim = head_dim; p.n_q = n_q; p.n_k = n_k;
   p.n_k_tiles = (n_k + KT - 1) / KT;
@@ -594,6 +597,8 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
     if (ndch == 2) RTTI_LAUNCH(80, 2, false);
     RTTI_LAUNCH(80, 3, false);
   }
+  if (use_v3)   // 64-key tiles, MMA look-ahead, one thread per row, 2 CTAs/SM (attn_self_v2.cu)
+    return launch_attn_self_v3(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.qk_src, lse, st);
   if (KT == 64) RTTI_LAUNCH(64, 1, false);
   if (ndch == 1 && g_v2 && !g_exp16)   // software-pipelined kernel (attn_self_v2.cu): 1 CTA/SM, MMAs hidden behind exps
     return launch_attn_self_v2(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.qk_src, lse, st);

@@ -259,3 +259,234 @@ int launch_attn_self_v2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
 }
 
 }  // namespace rtti
+
+// =====================================================================================================
+// v3: the same MMA look-ahead with 64-key tiles, ONE thread per query row and TWO CTAs per SM.
+//
+// v2 hides the MMAs but its 8 softmax warps run in lock-step (the two threads of a row exchange their max
+// through a named barrier every tile), so on every SM sub-partition both resident warps are in the MUFU burst
+// or outside it at the same time and the MUFU pipe idles ~45 % of the time. v3 removes the exchange (a thread
+// owns a whole row of a 64-key tile) and lets two independent CTAs per SM de-phase naturally: while one CTA's
+// warp on a sub-partition loads S / takes the max / stores P, the other CTA's warp keeps the MUFU pipe busy.
+// TMEM per CTA: S0 [0,64), S1 [64,128), O [128,192) -> 256-column allocation, two CTAs fill the 512 columns.
+namespace rtti {
+namespace v3 {
+constexpr int KT = 64;
+constexpr int NSTAGE = 4;
+constexpr int Q_TILE = 128 * 128;
+constexpr int KV_TILE = KT * 128;   // 8 KB
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + Q_TILE;
+constexpr int OFF_V = OFF_K + NSTAGE * KV_TILE;
+constexpr int OFF_O = OFF_V + NSTAGE * KV_TILE;
+constexpr int OFF_BAR = OFF_O + Q_TILE;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // ~98 KB -> 2 CTAs / SM
+constexpr uint32_t O_COL = 128;
+constexpr int THREADS = 192;
+}  // namespace v3
+
+__global__ void __launch_bounds__(v3::THREADS, 2)
+attn_self_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
+                    const AttnV2Params p) {
+  using namespace v3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // [4]
+  uint64_t* v_full = bars + 5;        // [4]
+  uint64_t* kv_empty = bars + 9;      // [4]
+  uint64_t* s_full = bars + 13;       // [2]
+  uint64_t* p_full = bars + 15;       // [2]
+  uint64_t* pv_done = bars + 17;
+  uint64_t* o_full = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int b_qk = p.qk_src[b];
+  const int nt = p.n_k_tiles;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); }
+    mbar_init(pv_done, 1); mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Q_TILE);
+      tma_load_4d(smem + OFF_Q, &tm_q, q_full, 0, h, q0, b_qk);
+      for (int j = 0; j < nt; ++j) {
+        const int st = j % NSTAGE;
+        mbar_wait(&kv_empty[st], ((j / NSTAGE) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], KV_TILE);
+        tma_load_4d(smem + OFF_K + st * KV_TILE, &tm_k, &k_full[st], 0, h, j * KT, b_qk);
+        mbar_expect_tx(&v_full[st], KV_TILE);
+        tma_load_4d(smem + OFF_V + st * KV_TILE, &tm_v, &v_full[st], 0, h, j * KT, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC_QK = umma_idesc_f16(128, KT, 0, 0);
+      constexpr uint32_t IDESC_PV = umma_idesc_f16(128, 64, 0, 1);
+      const uint32_t smem_base = smem_u32(smem);
+      auto issue_qk = [&](int j) {
+        const int st = j % NSTAGE;
+        mbar_wait(&k_full[st], (j / NSTAGE) & 1);
+        tc_fence_after();
+        for (int kk = 0; kk < p.ksteps_qk; ++kk) {
+          const uint64_t da = umma_desc_sw128(smem_base + OFF_Q + kk * 32, 0, 1024);
+          const uint64_t db = umma_desc_sw128(smem_base + OFF_K + st * KV_TILE + kk * 32, 0, 1024);
+          mma_f16_ss(tmem + 64u * (j & 1), da, db, IDESC_QK, kk > 0);
+        }
+        tc_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_qk(0);
+      for (int j = 0; j < nt; ++j) {
+        if (j + 1 < nt) issue_qk(j + 1);   // S[(j+1)&1] held P_{j-1}; PV_{j-1} precedes it in the in-order tensor pipe
+        const int st = j % NSTAGE;
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        mbar_wait(&v_full[st], (j / NSTAGE) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk) {
+          const uint64_t db = umma_desc_sw128(smem_base + OFF_V + st * KV_TILE + kk * 2048, KV_TILE, 1024);
+          mma_f16_ts(tmem + O_COL, tmem + 64u * (j & 1) + kk * 8, db, IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(&kv_empty[st]);
+        tc_commit(pv_done);
+        if (j == nt - 1) tc_commit(o_full);
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const bool row_ok = (q0 + row) < p.n_q;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t s_col = 64u * (j & 1);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      float s[64];
+      tmem_ld32(tlane + s_col, reinterpret_cast<uint32_t*>(s));
+      tmem_ld32(tlane + s_col + 32, reinterpret_cast<uint32_t*>(s) + 32);
+      tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s));
+      tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s) + 32);
+      const int valid = p.n_k - j * KT;
+      if (valid < KT) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i)
+          if (i >= valid) s[i] = -INFINITY;
+      }
+      float mx = s[0];
+#pragma unroll
+      for (int i = 1; i < KT; ++i) mx = fmaxf(mx, s[i]);
+      const float mxs = mx * p.scale_log2;
+      if (j == 0) {
+        m_ref = mxs;
+      } else {
+        const bool need = mxs > m_ref + 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(pv_done, (j - 1) & 1);   // O is being accumulated by PV_{j-1}
+          tc_fence_after();
+          const float alpha = need ? ex2_approx(m_ref - mxs) : 1.f;
+          if (need) m_ref = mxs;
+          l *= alpha;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tlane + O_COL + 16 * c, o);
+            tmem_wait_ld_regs16(o);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tlane + O_COL + 16 * c, o);
+          }
+        }
+      }
+      float rowsum = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e0 = ex2_approx(fmaf(s[2 * i], p.scale_log2, -m_ref));
+        const float e1 = ex2_approx(fmaf(s[2 * i + 1], p.scale_log2, -m_ref));
+        rowsum += e0 + e1;
+        pk[i] = pack_half2(e0, e1);
+      }
+      l += rowsum;
+      tmem_st32(tlane + s_col, pk);          // packed P_j over the first 32 columns of its own S buffer
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[j & 1]);
+    }
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    uint8_t* otile = smem + OFF_O + row * 128;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t o[32];
+      tmem_ld32(tlane + O_COL + 32 * hh, o);
+      tmem_wait_ld_regs32(o);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        uint4 w;
+        w.x = pack_half2(__uint_as_float(o[8 * v + 0]) * inv_l, __uint_as_float(o[8 * v + 1]) * inv_l);
+        w.y = pack_half2(__uint_as_float(o[8 * v + 2]) * inv_l, __uint_as_float(o[8 * v + 3]) * inv_l);
+        w.z = pack_half2(__uint_as_float(o[8 * v + 4]) * inv_l, __uint_as_float(o[8 * v + 5]) * inv_l);
+        w.w = pack_half2(__uint_as_float(o[8 * v + 6]) * inv_l, __uint_as_float(o[8 * v + 7]) * inv_l);
+        const int chunk = hh * 4 + v;
+        *reinterpret_cast<uint4*>(otile + ((chunk ^ (row & 7)) << 4)) = w;
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    if (threadIdx.x == 0) {
+      tma_store_4d(&tm_o, smem + OFF_O, 0, h, q0, b);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+    if (p.lse != nullptr && row_ok)
+      p.lse[(static_cast<size_t>(b) * p.heads + h) * p.n_q + q0 + row] = m_ref + log2f(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<256>(tmem);
+}
+
+int launch_attn_self_v3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                        int batch, int heads, int head_dim, int n_q, int n_k, float scale_log2, const int8_t* qk_src,
+                        float* lse, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_self_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) != cudaSuccess)
+      return RTTI_ERR_CUDA;
+    configured = true;
+  }
+  AttnV2Params p{};
+  p.batch = batch; p.heads = heads; p.head_dim = head_dim; p.n_q = n_q; p.n_k = n_k;
+  p.n_k_tiles = (n_k + v3::KT - 1) / v3::KT;
+  p.ksteps_qk = (head_dim + 15) / 16;
+  p.scale_log2 = scale_log2;
+  for (int i = 0; i < 64; ++i) p.qk_src[i] = qk_src[i];
+  p.lse = lse;
+  dim3 grid((n_q + 127) / 128, heads, batch);
+  attn_self_v3_kernel<<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
+}
+}  // namespace rtti

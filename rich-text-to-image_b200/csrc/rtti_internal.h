@@ -22,6 +22,11 @@ int launch_attn_self_v2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
                         int batch, int heads, int head_dim, int n_q, int n_k, float scale_log2, const int8_t* qk_src,
                         float* lse, cudaStream_t stream);
 
+// v3: 64-key tiles (K/V maps must be built with 64-row boxes), one thread per row, 2 CTAs/SM
+int launch_attn_self_v3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                        int batch, int heads, int head_dim, int n_q, int n_k, float scale_log2, const int8_t* qk_src,
+                        float* lse, cudaStream_t stream);
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace rtti

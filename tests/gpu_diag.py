@@ -194,6 +194,9 @@ CASES = {
     # packed-fp16-exponential variant of the head_dim<=64 kernel (experiment, off by default): RTTI_ATTN_EXP16=1
     "exp16:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
     "exp16:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
+    # v2 schedule (1 CTA/SM, 2 threads per row): RTTI_ATTN_V2=1
+    "v2:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    "v2:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
     # the sequential 2-CTA/SM kernel (v1) for head_dim <= 64: RTTI_ATTN_V1=1
     "v1:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
     "v1:self_inject": lambda: attn_case(4, 2, 64, 256, 256, qk_src=[0, 1, 1, 1]),
@@ -216,6 +219,8 @@ if __name__ == "__main__":
                 env["RTTI_ATTN_KT64"] = "1"; env["RTTI_ATTN_V1"] = "1"
             if name.startswith("v1:"):
                 env["RTTI_ATTN_V1"] = "1"
+            if name.startswith("v2:"):
+                env["RTTI_ATTN_V2"] = "1"
             r = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=120, capture_output=True, text=True, env=env)
             out = (r.stdout + r.stderr).strip()
             status = "ok" if r.returncode == 0 else f"rc={r.returncode}"

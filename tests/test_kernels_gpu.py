@@ -22,6 +22,8 @@ def test_kernel_case(case):
         env["RTTI_ATTN_KT64"] = "1"; env["RTTI_ATTN_V1"] = "1"
     if case.startswith("v1:"):
         env["RTTI_ATTN_V1"] = "1"
+    if case.startswith("v2:"):
+        env["RTTI_ATTN_V2"] = "1"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gpu_diag.py"), case], capture_output=True, text=True,
                        timeout=300, env=env)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
