@@ -83,6 +83,10 @@ int rtti_groupnorm_silu_fwd(const void* x, const void* chan_bias, const void* ga
                             float* workspace, int batch, int hw, int c, int groups, float eps, int apply_silu,
                             void* stream);
 
+/* out[rows, c] = a + b + bias[c] (fp16; bias may be NULL): the residual add of ResnetBlock2D
+ * (models/resnet.py:637-643) fused with the bias of conv2. */
+int rtti_add_bias_f16(const void* a, const void* b, const void* bias, void* out, long long rows, int c, void* stream);
+
 /* LayerNorm over the last dimension of x[rows, c] fp16 (models/attention.py:150,168,181). */
 int rtti_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int rows, int c, float eps,
                        void* stream);

@@ -389,6 +389,23 @@ __global__ void predict_x0_kernel(const __half* __restrict__ xt, const __half* _
   if (i < n) x0[i] = __float2half_rn((__half2float(xt[i]) - __half2float(eps[i]) * sq1ma) * inv_sqa);
 }
 
+// out[r, c] = a[r, c] + b[r, c] + bias[c]  (fp16; residual add of a resnet block fused with the conv2 bias, which
+// PyTorch otherwise adds to a channels-last convolution output in a separate broadcast pass)
+__global__ void add_bias_f16_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
+                                    const __half* __restrict__ bias, __half* __restrict__ out, long long nvec, int cvec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8], z[8];
+    unpack8(reinterpret_cast<const Half8*>(a)[i], x);
+    unpack8(reinterpret_cast<const Half8*>(b)[i], y);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z[k] = 0.f;
+    if (bias) unpack8(reinterpret_cast<const Half8*>(bias)[i % cvec], z);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = x[k] + y[k] + z[k];
+    reinterpret_cast<Half8*>(out)[i] = pack8(x);
+  }
+}
+
 static inline int ok_or_cuda() { return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA; }
 
 }  // namespace rtti
@@ -516,5 +533,18 @@ extern "C" int rtti_predict_x0(const void* x_t, const void* eps, float alpha, vo
   if (!x_t || !eps || !x0 || n < 1 || !(alpha > 0.f) || alpha > 1.f) return RTTI_ERR_ARG;
   predict_x0_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)x_t, (const __half*)eps, sqrtf(1.f - alpha), 1.f / sqrtf(alpha), (__half*)x0, n);
+  return ok_or_cuda();
+}
+
+extern "C" int rtti_add_bias_f16(const void* a, const void* b, const void* bias, void* out, long long rows, int c,
+                                 void* stream) {
+  if (!a || !b || !out || rows < 1 || c < 8) return RTTI_ERR_ARG;
+  if (c % 8 != 0) return RTTI_ERR_SHAPE;
+  if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out | (uintptr_t)bias) & 15) return RTTI_ERR_ALIGN;
+  const long long nvec = rows * (c / 8);
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  add_bias_f16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, (const __half*)bias,
+                                                                     (__half*)out, nvec, c / 8);
   return ok_or_cuda();
 }

@@ -317,3 +317,16 @@ def add_bias_f32(a, b, bias=None):
     _lib.check(lib.rtti_add_bias_f32(_ptr(a), _ptr(b), _ptr(bias), _ptr(out), a.numel() // C, C, _stream()), "rtti_add_bias_f32")
     _count(1)
     return out
+
+
+def add_bias_f16(a, b, bias=None, out=None):
+    """a + b + bias[c] for fp16 [.., C] tensors (rtti_add_bias_f16); `out` may alias `b`."""
+    lib = _lib.load()
+    _req(a, _F16, "a"); _req(b, _F16, "b")
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    C = a.shape[-1]
+    if out is None:
+        out = torch.empty_like(a)
+    _lib.check(lib.rtti_add_bias_f16(_ptr(a), _ptr(b), _ptr(bias), _ptr(out), a.numel() // C, C, _stream()), "rtti_add_bias_f16")
+    _count(1)
+    return out

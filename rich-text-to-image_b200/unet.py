@@ -173,10 +173,12 @@ class LayerNormCL(nn.Module):
 class Conv2dCL(nn.Conv2d):
     """nn.Conv2d over channels-last activations given as [B, H, W, C] (cuDNN NHWC path)."""
 
-    def forward_cl(self, x, H, W):
+    def forward_cl(self, x, H, W, with_bias=True):
+        """with_bias=False: the caller folds self.bias into the consumer (the next GroupNorm's per-channel bias or the
+        fused residual add) — PyTorch adds the bias of a channels-last convolution in a separate broadcast pass."""
         B = x.shape[0]
         x4 = x.view(B, H, W, -1).permute(0, 3, 1, 2)  # logical NCHW, channels_last memory: no copy
-        y = F.conv2d(x4, self.weight, self.bias, self.stride, self.padding)
+        y = F.conv2d(x4, self.weight, self.bias if with_bias else None, self.stride, self.padding)
         Ho, Wo = y.shape[2], y.shape[3]
         y = y.permute(0, 2, 3, 1)
         if not y.is_contiguous():
@@ -303,16 +305,17 @@ class ResnetBlock2D(nn.Module):
     def forward(self, x, H, W, temb_act, feature_idx=None):
         """x [B, HW, Cin]; temb_act = silu(temb). Returns output [B, HW, Cout] (resnet.py:591-645)."""
         h = self.norm1(x, silu=True)
-        h, _, _ = self.conv1.forward_cl(h, H, W)
-        t = F.linear(temb_act, self.time_emb_proj.weight, self.time_emb_proj.bias)
-        h = self.norm2(h, silu=True, chan_bias=t.contiguous())  # `hidden_states + temb` fused into the norm
-        h, _, _ = self.conv2.forward_cl(h, H, W)
+        h, _, _ = self.conv1.forward_cl(h, H, W, with_bias=False)
+        # conv1 bias + `hidden_states + temb` (resnet.py:621-622) both folded into norm2 as a per-(batch, channel) bias
+        t = F.linear(temb_act, self.time_emb_proj.weight, self.time_emb_proj.bias + self.conv1.bias)
+        h = self.norm2(h, silu=True, chan_bias=t.contiguous())
+        h, _, _ = self.conv2.forward_cl(h, H, W, with_bias=False)
         if feature_idx is not None:
             # inject_states of the reference pass replaces the residual branch (resnet.py:639-641)
             h = h.index_select(0, feature_idx)
         if self.conv_shortcut is not None:
             x = F.linear(x, self.conv_shortcut.weight.view(self.conv_shortcut.weight.shape[0], -1), self.conv_shortcut.bias)
-        return h.add_(x)
+        return ops.add_bias_f16(x, h, self.conv2.bias, out=h)   # residual + conv2 bias in one pass
 
 
 class Downsample2D(nn.Module):
