@@ -320,12 +320,19 @@ class RegionDiffusionXL:
             ev[1].record()
         dt = self.scheduler.dt(t)
         step_ref = st.inject and (st.inject_selfattn > 0 or background_inject_step)                       # :830-841
+        ex = None
         if plan.world > 1 and self.fused_exchange:
-            # fused all-gather + blend + CFG + Euler over NVLink peer memory (csrc/gather_blend.cu)
             xkey = (tuple(p["kind"] for p in passes), st.latents[0].numel())
             if xkey not in self._exchanges:   # symmetric buffers are allocated once per problem shape
-                self._exchanges[xkey] = region_parallel.PeerExchange(passes, st.latents[0].numel(), self.device)
-            ex = self._exchanges[xkey]
+                try:
+                    self._exchanges[xkey] = region_parallel.PeerExchange(passes, st.latents[0].numel(), self.device)
+                except Exception as e:        # no peer-mappable memory (e.g. GPUs without P2P): NCCL all-gather path
+                    import warnings
+                    warnings.warn(f"rtti_b200: symmetric peer memory unavailable ({e!r}); using the NCCL all-gather exchange")
+                    self.fused_exchange = False
+            ex = self._exchanges.get(xkey)
+        if ex is not None:
+            # fused all-gather + blend + CFG + Euler over NVLink peer memory (csrc/gather_blend.cu)
             _, owner = plan._plan(feat_inject_step)
             sid = ex.publish(eps_local, local, owner)
             st.noise_pred, st.latents, ref_out = ops.gather_blend_step(
