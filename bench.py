@@ -29,6 +29,10 @@ PASSES_PER_STEP = 2 + 2 + (N_REGIONS - 1)
 UNET_PASS_GFLOP = 6761.2  # SURVEY §8d [probe], batch-1 SDXL UNet forward
 
 
+WORKLOAD = ("SDXL 1024x1024 font-color example shape: 5 region prompts, color_guidance_weight=1, inject_selfattn=0.5, "
+            "inject_background=0.5, 8 UNet passes/step, 41-step Euler schedule")
+
+
 def synth_workload(device):
     import torch
     g = torch.Generator().manual_seed(7)
@@ -170,7 +174,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "denoising steps/sec SDXL 1024^2 5-region", "value": v, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SDXL 1024x1024, 5 region prompts, inject_selfattn=0.5, inject_background=0.5, 8 UNet passes/step"},
+        "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -304,8 +308,7 @@ def run_product(args, rank, world, local_rank):
         "metric": "denoising steps/sec SDXL 1024^2 5-region", "value": steps_per_s, "unit": "steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "SDXL 1024x1024 font-color example shape: 5 region prompts, color_guidance_weight=1, "
-                               "inject_selfattn=0.5, inject_background=0.5, 8 UNet passes/step (one batched call), 41-step Euler schedule",
+        "config": {"workload": WORKLOAD, "execution": "the 8 passes run as one batched, CUDA-graph-replayed UNet call",
                    "l2": "inputs larger than L2: 5.1 GB of fp16 UNet weights stream every step",
                    "parallelism": f"region-parallel x{world}" if world > 1 else "single GPU",
                    "unet_tflop_per_step": PASSES_PER_STEP * UNET_PASS_GFLOP / 1e3,
