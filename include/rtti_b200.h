@@ -169,6 +169,33 @@ int rtti_gather_blend_step(const void* const* peer_slots, void* const* peer_flag
                            const void* latents_ref, void* latents_ref_out, float dt_sigma, unsigned int step_id,
                            void* stream);
 
+/* Stripe-parallel colour guidance (multi-GPU; new relative to the single-GPU reference, which back-propagates
+ * through the batch-1 VAE decoder on one device: models/region_diffusion_sdxl.py:849-867). Every activation of
+ * the decoder's up-blocks is split by image rows over `world` ranks.
+ *
+ * rtti_gn32_silu_fwd/bwd_striped: GroupNorm(+SiLU) over a tensor of hw_total rows of which x holds this rank's
+ *   hw_local rows (batch 1, groups <= 32). The statistics are reduced through peer memory inside the call:
+ *   peer_sums (host, [world]): device pointers to each rank's fp32 [2 (seq parity)][2*groups] slot;
+ *   peer_flags (host, [world]): device pointers to each rank's uint32 {sequence, error} words (zero-initialised);
+ *   seq: 1, 2, 3, ... the same on every rank for the same call. All ranks obtain bit-identical statistics.
+ *   workspace: fp32 [rtti_gn32_workspace_elems(1, hw_local, c, groups)].
+ * rtti_halo_exchange: pad_local is this rank's conv input [1 + rows + 1][row_elems] fp32 with the interior rows
+ *   already written; pushes the first / last interior row into the bottom / top halo row of pad_up / pad_down
+ *   (peer-mapped pointers to the neighbours' buffers of the same shape; NULL at the image border, where the own
+ *   halo row is zeroed instead), then waits until both neighbours have pushed theirs.
+ *   flags_*: uint32[4] per rank {from_up, from_down, error, arrival counter}, zero-initialised, peer-mapped.
+ */
+int rtti_gn32_silu_fwd_striped(const float* x, const float* chan_bias, const float* gamma, const float* beta, float* y,
+                               float* mean_rstd, float* workspace, int hw_local, long long hw_total, int c, int groups,
+                               float eps, int apply_silu, void* const* peer_sums, void* const* peer_flags, int world,
+                               int rank, unsigned int seq, void* stream);
+int rtti_gn32_silu_bwd_striped(const float* x, const float* chan_bias, const float* dz, const float* gamma,
+                               const float* beta, const float* mean_rstd, float* dx, float* workspace, int hw_local,
+                               long long hw_total, int c, int groups, int apply_silu, void* const* peer_sums,
+                               void* const* peer_flags, int world, int rank, unsigned int seq, void* stream);
+int rtti_halo_exchange(float* pad_local, float* pad_up, float* pad_down, int rows, long long row_elems,
+                       void* flags_local, void* flags_up, void* flags_down, unsigned int seq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

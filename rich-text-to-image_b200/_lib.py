@@ -47,6 +47,13 @@ SIGNATURES = {
     "rtti_gather_blend_step": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_int, c_int, P_int, c_int, c_int,
                                        c_void_p, c_ll, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                        ctypes.c_uint, c_void_p]),
+    "rtti_gn32_silu_fwd_striped": (c_int, [c_void_p] * 7 + [c_int, c_ll, c_int, c_int, c_float, c_int,
+                                           ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_int, c_int, ctypes.c_uint,
+                                           c_void_p]),
+    "rtti_gn32_silu_bwd_striped": (c_int, [c_void_p] * 8 + [c_int, c_ll, c_int, c_int, c_int,
+                                           ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_int, c_int, ctypes.c_uint,
+                                           c_void_p]),
+    "rtti_halo_exchange": (c_int, [c_void_p] * 3 + [c_int, c_ll] + [c_void_p] * 3 + [ctypes.c_uint, c_void_p]),
 }
 
 _lib = None

@@ -7,6 +7,7 @@
 //   backward: dy = dz * silu'(y) (y recomputed), partial (sum dy*gamma, sum dy*gamma*xhat) -> finalize ->
 //             dx = rstd * (dy*gamma - c1 - xhat*c2)
 // Deterministic (fixed-order two-stage reductions, no atomics); 128-bit vector accesses.
+#include "peer_sync.cuh"
 #include "rtti_internal.h"
 
 namespace rtti {
@@ -227,6 +228,80 @@ static int gn32_check(const void* a, const void* b_, const void* c_, const void*
   return RTTI_OK;
 }
 
+// ---- stripe-parallel variant (multi-GPU colour guidance, see stripe_exchange.cu) -----------------------------
+struct PeerSums {
+  float* sums[PEER_MAX_WORLD];          // per rank: float [2 parities][2 * groups], peer-mapped
+  unsigned int* flags[PEER_MAX_WORLD];  // per rank: [0] sequence word, [1] error word
+  int world, rank;
+  unsigned int seq;
+};
+
+// One CTA, one warp per group, batch 1: reduce this rank's chunk partials, publish the raw sums, wait for every
+// peer, add the slots in RANK ORDER (bit-identical statistics on all ranks).
+// MODE 0 -> out = (mean, rstd);  MODE 1 -> out = (c1, c2) = sums / n_total
+template <int MODE>
+__global__ void __launch_bounds__(1024) gn32_finalize_peer_kernel(const float* __restrict__ ws, float* __restrict__ out,
+                                                                  const PeerSums pp, int groups, int chunks,
+                                                                  float n_total, float eps) {
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int par = (int)(pp.seq & 1u);
+  if (g < groups) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = lane; k < chunks; k += 32) {
+      const float* o = ws + ((size_t)k * groups + g) * 2;
+      s0 += o[0]; s1 += o[1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) {
+      float* mine = pp.sums[pp.rank] + (size_t)par * 2 * groups;
+      mine[2 * g] = s0; mine[2 * g + 1] = s1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(pp.flags[pp.rank], pp.seq);
+  }
+  if (threadIdx.x < pp.world && threadIdx.x != pp.rank) {
+    if (!wait_seq(pp.flags[threadIdx.x], pp.seq)) pp.flags[pp.rank][1] = 0xDEADu;
+  }
+  __syncthreads();
+  if (g < groups && lane == 0) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int r = 0; r < pp.world; ++r) {
+      const float* p = pp.sums[r] + (size_t)par * 2 * groups;
+      t0 += ld_volatile_f32(p + 2 * g);
+      t1 += ld_volatile_f32(p + 2 * g + 1);
+    }
+    float* d = out + (size_t)g * 2;
+    if (MODE == 0) {
+      const float mean = t0 / n_total;
+      const float var = fmaxf(t1 / n_total - mean * mean, 0.f);
+      d[0] = mean; d[1] = rsqrtf(var + eps);
+    } else {
+      d[0] = t0 / n_total; d[1] = t1 / n_total;
+    }
+  }
+}
+
+static int fill_peer_sums(PeerSums& pp, void* const* peer_sums, void* const* peer_flags, int world, int rank,
+                          unsigned int seq) {
+  if (!peer_sums || !peer_flags) return RTTI_ERR_ARG;
+  if (world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world) return RTTI_ERR_ARG;
+  for (int r = 0; r < world; ++r) {
+    if (!peer_sums[r] || !peer_flags[r]) return RTTI_ERR_ARG;
+    if (((uintptr_t)peer_sums[r] | (uintptr_t)peer_flags[r]) & 3) return RTTI_ERR_ALIGN;
+    pp.sums[r] = (float*)peer_sums[r];
+    pp.flags[r] = (unsigned int*)peer_flags[r];
+  }
+  pp.world = world; pp.rank = rank; pp.seq = seq;
+  return RTTI_OK;
+}
+
 }  // namespace rtti
 
 using namespace rtti;
@@ -275,6 +350,59 @@ extern "C" int rtti_gn32_silu_bwd(const float* x, const float* chan_bias, const 
                                                                          (float)hw * (float)(c / groups), 0.f);
   gn32_apply_kernel<1><<<grid, p.threads, 0, st>>>(x, chan_bias, dz, gamma, beta, mean_rstd, c12, dx, hw, c, groups, p.nvec,
                                                    p.rowlanes, p.rows_per_chunk, apply_silu);
+  return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
+}
+
+
+extern "C" int rtti_gn32_silu_fwd_striped(const float* x, const float* chan_bias, const float* gamma, const float* beta,
+                                          float* y, float* mean_rstd, float* workspace, int hw_local, long long hw_total,
+                                          int c, int groups, float eps, int apply_silu, void* const* peer_sums,
+                                          void* const* peer_flags, int world, int rank, unsigned int seq, void* stream) {
+  int rc = gn32_check(x, gamma, beta, y, 1, hw_local, c, groups);
+  if (rc != RTTI_OK) return rc;
+  if (!mean_rstd || !workspace || hw_total < hw_local) return RTTI_ERR_ARG;
+  if (groups > 32) return RTTI_ERR_SHAPE;
+  PeerSums pp{};
+  rc = fill_peer_sums(pp, peer_sums, peer_flags, world, rank, seq);
+  if (rc != RTTI_OK) return rc;
+  const GN32Plan p = gn32_plan(1, hw_local, c);
+  const size_t smem = (size_t)p.rowlanes * c * 2 * sizeof(float);
+  if (smem > 48 * 1024) return RTTI_ERR_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(p.chunks, 1);
+  gn32_partial_kernel<0><<<grid, p.threads, smem, st>>>(x, chan_bias, nullptr, gamma, beta, nullptr, workspace, hw_local, c,
+                                                        groups, p.nvec, p.rowlanes, p.rows_per_chunk, p.chunks, 0);
+  gn32_finalize_peer_kernel<0><<<1, 32 * groups, 0, st>>>(workspace, mean_rstd, pp, groups, p.chunks,
+                                                          (float)hw_total * (float)(c / groups), eps);
+  gn32_apply_kernel<0><<<grid, p.threads, 0, st>>>(x, chan_bias, nullptr, gamma, beta, mean_rstd, nullptr, y, hw_local, c,
+                                                   groups, p.nvec, p.rowlanes, p.rows_per_chunk, apply_silu);
+  return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
+}
+
+extern "C" int rtti_gn32_silu_bwd_striped(const float* x, const float* chan_bias, const float* dz, const float* gamma,
+                                          const float* beta, const float* mean_rstd, float* dx, float* workspace,
+                                          int hw_local, long long hw_total, int c, int groups, int apply_silu,
+                                          void* const* peer_sums, void* const* peer_flags, int world, int rank,
+                                          unsigned int seq, void* stream) {
+  int rc = gn32_check(x, gamma, beta, dx, 1, hw_local, c, groups);
+  if (rc != RTTI_OK) return rc;
+  if (!dz || !mean_rstd || !workspace || ((uintptr_t)dz & 15) || hw_total < hw_local) return RTTI_ERR_ARG;
+  if (groups > 32) return RTTI_ERR_SHAPE;
+  PeerSums pp{};
+  rc = fill_peer_sums(pp, peer_sums, peer_flags, world, rank, seq);
+  if (rc != RTTI_OK) return rc;
+  const GN32Plan p = gn32_plan(1, hw_local, c);
+  const size_t smem = (size_t)p.rowlanes * c * 2 * sizeof(float);
+  if (smem > 48 * 1024) return RTTI_ERR_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(p.chunks, 1);
+  float* c12 = workspace + (size_t)p.chunks * groups * 2;
+  gn32_partial_kernel<1><<<grid, p.threads, smem, st>>>(x, chan_bias, dz, gamma, beta, mean_rstd, workspace, hw_local, c,
+                                                        groups, p.nvec, p.rowlanes, p.rows_per_chunk, p.chunks, apply_silu);
+  gn32_finalize_peer_kernel<1><<<1, 32 * groups, 0, st>>>(workspace, c12, pp, groups, p.chunks,
+                                                          (float)hw_total * (float)(c / groups), 0.f);
+  gn32_apply_kernel<1><<<grid, p.threads, 0, st>>>(x, chan_bias, dz, gamma, beta, mean_rstd, c12, dx, hw_local, c, groups,
+                                                   p.nvec, p.rowlanes, p.rows_per_chunk, apply_silu);
   return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
 }
 

@@ -307,13 +307,65 @@ def gn32_silu_bwd(x, dz, gamma, beta, stats, groups, silu, chan_bias=None):
     return dx
 
 
-def add_bias_f32(a, b, bias=None):
-    """a + b + bias[c] for fp32 [.., C] tensors (rtti_add_bias_f32)."""
+def gn32_silu_fwd_striped(x, gamma, beta, groups, eps, silu, hw_total, peers, seq, chan_bias=None, out=None):
+    """Stripe-parallel gn32_silu_fwd: x [1, hw_local, C] holds this rank's rows of a [1, hw_total, C] tensor; the
+    statistics are reduced over the ranks through peer memory (rtti_gn32_silu_fwd_striped). `peers` provides
+    sum_ptrs / gn_flag_ptrs (ctypes arrays), world, rank. `out` may be a contiguous view (e.g. a pad interior)."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    assert x.dim() == 3 and x.shape[0] == 1 and x.is_contiguous()
+    _, HW, C = x.shape
+    y = torch.empty_like(x) if out is None else out
+    assert y.is_contiguous() and y.numel() == x.numel() and y.dtype == torch.float32
+    stats = torch.empty(1, groups, 2, dtype=torch.float32, device=x.device)
+    rc = lib.rtti_gn32_silu_fwd_striped(_ptr(x), _ptr(chan_bias), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats),
+                                        _ptr(_gn32_workspace(x, groups)), HW, int(hw_total), C, groups, float(eps),
+                                        1 if silu else 0, peers.sum_ptrs, peers.gn_flag_ptrs, peers.world, peers.rank,
+                                        int(seq), _stream())
+    _lib.check(rc, "rtti_gn32_silu_fwd_striped")
+    _count(3)
+    return y, stats
+
+
+def gn32_silu_bwd_striped(x, dz, gamma, beta, stats, groups, silu, hw_total, peers, seq, chan_bias=None, out=None):
+    """Input gradient of gn32_silu_fwd_striped (rtti_gn32_silu_bwd_striped)."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x"); _req(dz, torch.float32, "dz")
+    assert x.is_contiguous() and dz.is_contiguous() and dz.numel() == x.numel() and x.shape[0] == 1
+    _, HW, C = x.shape
+    dx = torch.empty_like(x) if out is None else out
+    assert dx.is_contiguous() and dx.numel() == x.numel() and dx.dtype == torch.float32
+    rc = lib.rtti_gn32_silu_bwd_striped(_ptr(x), _ptr(chan_bias), _ptr(dz), _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(dx),
+                                        _ptr(_gn32_workspace(x, groups)), HW, int(hw_total), C, groups, 1 if silu else 0,
+                                        peers.sum_ptrs, peers.gn_flag_ptrs, peers.world, peers.rank, int(seq), _stream())
+    _lib.check(rc, "rtti_gn32_silu_bwd_striped")
+    _count(3)
+    return dx
+
+
+def halo_exchange(pad, pad_ptr_up, pad_ptr_down, flags_local, flags_up, flags_down, seq):
+    """pad [rows + 2, W, C] fp32 (interior rows written): push the boundary rows into the neighbours' halo rows and
+    wait for theirs (rtti_halo_exchange). pad_ptr_up / pad_ptr_down: peer-mapped addresses of the neighbours' pads
+    (0 at the image border)."""
+    lib = _lib.load()
+    _req(pad, torch.float32, "pad")
+    assert pad.dim() == 3 and pad.is_contiguous()
+    rows = pad.shape[0] - 2
+    rc = lib.rtti_halo_exchange(_ptr(pad), ctypes.c_void_p(pad_ptr_up or 0), ctypes.c_void_p(pad_ptr_down or 0), rows,
+                                pad.shape[1] * pad.shape[2], ctypes.c_void_p(flags_local),
+                                ctypes.c_void_p(flags_up or 0), ctypes.c_void_p(flags_down or 0), int(seq), _stream())
+    _lib.check(rc, "rtti_halo_exchange")
+    _count(1)
+
+
+def add_bias_f32(a, b, bias=None, out=None):
+    """a + b + bias[c] for fp32 [.., C] tensors (rtti_add_bias_f32); `out` may alias a or b."""
     lib = _lib.load()
     _req(a, torch.float32, "a"); _req(b, torch.float32, "b")
     assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
     C = a.shape[-1]
-    out = torch.empty_like(a)
+    if out is None:
+        out = torch.empty_like(a)
     _lib.check(lib.rtti_add_bias_f32(_ptr(a), _ptr(b), _ptr(bias), _ptr(out), a.numel() // C, C, _stream()), "rtti_add_bias_f32")
     _count(1)
     return out

@@ -64,6 +64,8 @@ class RegionDiffusionXL:
         self.use_cuda_graphs = True  # replay the batched UNet pass of a step as one CUDA graph (launch-bound otherwise)
         self.profile_events = None   # dict -> CUDA-event pairs per phase of a step (bench.py breakdown)
         self.fused_exchange = True   # multi-GPU: fused peer-memory gather+blend kernel instead of NCCL all-gather
+        self.stripe_guidance = True  # multi-GPU: colour guidance (VAE fwd+bwd) split by image rows over the ranks
+        self._stripe_engines = {}
         self.last_step_stats = {}
 
     @classmethod
@@ -126,10 +128,31 @@ class RegionDiffusionXL:
             self.last_step_stats["color_loss"] = loss
             return g[None]
 
-        grad_lat = vae_guidance.image_and_latent_grad(self.vae, x0.float() / sf, grad_image) / (sf * math.sqrt(alpha))
+        grad_lat = vae_guidance.image_and_latent_grad(self.vae, x0.float() / sf, grad_image,
+                                                      engine=self._stripe_engine(x0)) / (sf * math.sqrt(alpha))
         atten_all = tfd["color_obj_atten_all"].to(self.device, torch.float32).expand_as(grad_lat).contiguous()
         return ops.latent_guidance_update(latents.contiguous(), grad_lat.contiguous(), atten_all,
                                           float(tfd["color_guidance_weight"]))
+
+    def _stripe_engine(self, x0):
+        """Stripe-parallel VAE engine (stripe_parallel.py) when running on >1 GPU, else None (single-GPU engine)."""
+        import torch.distributed as dist
+        if not (self.stripe_guidance and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return None
+        from .vae import AutoencoderKLDecoder
+        h, w = int(x0.shape[2]), int(x0.shape[3])
+        if not isinstance(self.vae, AutoencoderKLDecoder) or x0.shape[0] != 1 or h % dist.get_world_size() != 0:
+            return None
+        if (h, w) not in self._stripe_engines:   # symmetric arena allocated once per latent shape
+            try:
+                from .stripe_parallel import StripedDecoderFwdBwd
+                self._stripe_engines[(h, w)] = StripedDecoderFwdBwd(self.vae, h, w, self.device)
+            except Exception as e:               # no peer-mappable memory: replicated guidance
+                import warnings
+                warnings.warn(f"rtti_b200: stripe-parallel colour guidance unavailable ({e!r}); running it replicated")
+                self.stripe_guidance = False
+                return None
+        return self._stripe_engines[(h, w)]
 
     # ------------------------------------------------------------------ sampling
     @torch.no_grad()
@@ -373,4 +396,6 @@ class RegionDiffusionXL:
                 callback(i, t, st.latents)
         for ex in self._exchanges.values():
             ex.check()
+        for eng in self._stripe_engines.values():
+            eng.arena.check()
         return st.latents

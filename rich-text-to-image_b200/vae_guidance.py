@@ -185,13 +185,14 @@ class DecoderFwdBwd:
             torch.backends.cuda.matmul.allow_tf32 = prev
 
 
-def image_and_latent_grad(vae, z, grad_fn):
+def image_and_latent_grad(vae, z, grad_fn, engine=None):
     """image = decode(z); grad_image = grad_fn(image.detach()); returns d/dz of <grad_image, decode(z)>.
     Uses the explicit forward/backward for vae.AutoencoderKLDecoder and autograd for any other decoder object
-    exposing decode_tensor() (e.g. the tiny stand-in of the parity fixtures)."""
+    exposing decode_tensor() (e.g. the tiny stand-in of the parity fixtures). `engine`: a
+    stripe_parallel.StripedDecoderFwdBwd to run the decoder split by rows over the ranks."""
     from .vae import AutoencoderKLDecoder
     if isinstance(vae, AutoencoderKLDecoder):
-        eng = getattr(vae, "_fwd_bwd", None)
+        eng = engine if engine is not None else getattr(vae, "_fwd_bwd", None)
         if eng is None:
             eng = vae._fwd_bwd = DecoderFwdBwd(vae)
         img = eng.forward(z)

@@ -4,7 +4,8 @@
 
 Every rank runs the tiny SDXL-shaped rich-text loop (3 regions, injection, font sizes, colour guidance) with
 (a) the fused peer-memory gather+blend kernel and (b) the NCCL all-gather baseline, and compares both with the
-golden latents produced by the unmodified single-process reference (tests/golden/xl_loops.npz)."""
+golden latents produced by the unmodified single-process reference (tests/golden/xl_loops.npz); then the
+stripe-parallel colour-guidance engine is compared with the single-GPU one."""
 import os
 import sys
 
@@ -15,6 +16,52 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tests import synth  # noqa: E402
+
+
+def check_stripe_guidance(rank, world):
+    """Stripe-parallel VAE forward + backward (stripe_parallel.py) against the single-GPU engine on the same
+    inputs: a small decoder (2 calls: buffer re-use across calls) and the SDXL-size one (timed)."""
+    from rtti_b200.stripe_parallel import StripedDecoderFwdBwd
+    from rtti_b200.vae import AutoencoderKLDecoder, VAEConfig
+    from rtti_b200.vae_guidance import DecoderFwdBwd
+    ok = True
+    for name, cfg, hw, reps in (("small", VAEConfig(block_out_channels=(32, 64, 128, 128)), 32, 2),
+                                ("sdxl", VAEConfig.sdxl(), 128, 3)):
+        vae = AutoencoderKLDecoder(cfg).init_synthetic(seed=5).finalize("cuda")
+        ref_eng = DecoderFwdBwd(vae)
+        eng = StripedDecoderFwdBwd(vae, hw, hw, torch.device("cuda"))
+        gen = torch.Generator().manual_seed(11)
+        for rep in range(reps):
+            z = torch.randn(1, 4, hw, hw, generator=gen).cuda()
+            wgt = torch.randn(1, 3, hw * 8, hw * 8, generator=gen).cuda()
+            grad_fn = lambda img: torch.tanh(img) * wgt
+            img_r = ref_eng.forward(z)
+            g_r = ref_eng.backward(grad_fn(img_r))
+            torch.cuda.synchronize()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            img_s = eng.forward(z)
+            g_s = eng.backward(grad_fn(img_s))
+            e1.record()
+            img_r = ref_eng.forward(z)
+            g_r = ref_eng.backward(grad_fn(img_r))
+            e2.record()
+            torch.cuda.synchronize()
+            eng.arena.check()
+            e_img = float((img_s - img_r).abs().max() / img_r.abs().max())
+            e_g = float((g_s - g_r).abs().max() / g_r.abs().max())
+            gathered = [torch.empty_like(g_s) for _ in range(world)]
+            dist.all_gather(gathered, g_s.contiguous())
+            same = all(torch.equal(gathered[0], x) for x in gathered)
+            good = e_img < 2e-3 and e_g < 5e-3 and same and bool(torch.isfinite(g_s).all())
+            ok &= good
+            if rank == 0:
+                print(f"stripe guidance [{name}] world={world} rep={rep}: image rel err {e_img:.2e}, latent-grad rel err {e_g:.2e}, "
+                      f"ranks bit-identical: {same}, striped {e0.elapsed_time(e1):.2f} ms vs replicated {e1.elapsed_time(e2):.2f} ms "
+                      f"({'OK' if good else 'FAIL'})", flush=True)
+        del eng, ref_eng, vae
+        torch.cuda.empty_cache()
+    return ok
 
 
 def main():
@@ -58,6 +105,7 @@ def main():
         if rank == 0:
             print(f"world={world} fused_exchange={fused}: max err vs reference golden {err.max().item():.4f} "
                   f"({'OK' if good else 'FAIL'}), ranks bit-identical: {same}", flush=True)
+    ok &= check_stripe_guidance(rank, world)
     if rank == 0:
         d = (results[True] - results[False]).abs().max().item()
         print(f"fused vs NCCL path max |diff| = {d:.3e}", flush=True)
