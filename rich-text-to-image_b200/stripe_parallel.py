@@ -5,21 +5,24 @@ The reference back-propagates the colour loss through the batch-1 fp32 VAE decod
 (models/region_diffusion_sdxl.py:849-867). With region-parallel UNet passes that replicated 51 ms is what limits
 scaling (Amdahl), so here:
 
-  * post_quant_conv, conv_in and the mid block (16 384-token attention, 4 % of the decoder FLOPs) stay replicated;
-  * from the first up-block on, every rank owns `rows` consecutive image rows of every activation. 3x3 convolutions
+  * post_quant_conv and conv_in (0.6 GFLOP) stay replicated;
+  * from the mid block on, every rank owns `rows` consecutive image rows of every activation. The 16 384-token
+    mid-block attention runs this rank's query rows against all keys/values (normalised input all-gathered, the
+    K/V-side gradient reduce-scattered after its projection: one 32 MB collective each way). 3x3 convolutions
     read padded buffers [1 + rows + 1, W, C] living in a symmetric (peer-mapped) arena whose halo rows the
     neighbours fill with ONE kernel per convolution (rtti_halo_exchange); GroupNorm statistics are reduced inside
     the GroupNorm call through peer memory (rtti_gn32_silu_*_striped); nearest-neighbour upsampling, SiLU, residual
     adds and 1x1 shortcuts are stripe-local;
   * the data gradient of a 3x3 convolution is evaluated as a forward convolution of the (haloed) output gradient
     with the flipped, transposed filter — the same halo machinery serves both directions;
-  * two NCCL all-gathers per call (the decoded image stripes: 12.6 MB, and the gradient entering the mid block:
+  * two more NCCL all-gathers per call (the decoded image stripes: 12.6 MB, and the gradient entering conv_in:
     32 MB) and one 256 KB broadcast of the final latent gradient from rank 0, which keeps the replicated latents
     bit-identical on all ranks whatever algorithms cuDNN picked per rank.
 
 PyTorch is used for the rendezvous (symmetric memory), cuDNN convolutions and the NCCL calls.
 """
 import ctypes
+import math
 
 import torch
 import torch.nn.functional as F
@@ -183,6 +186,37 @@ class StripedDecoderFwdBwd(DecoderFwdBwd):
             return ops.add_bias_f32(dx, self._conv_b(r.conv_shortcut, g, cin, rows, W))
         return ops.add_bias_f32(dx, g.contiguous())
 
+    def _s_attn_f(self, a, x, hw_total, tape):
+        """Mid-block attention with this rank's stripe of queries against all keys/values: GroupNorm striped, the
+        normalised activations all-gathered (32 MB) for K/V, probabilities [T/world, T] materialised per rank."""
+        _, Tl, C = x.shape
+        hn = self._s_gn_f(a.group_norm, x, False, tape, hw_total)
+        hn_full = torch.empty(1, hw_total, C, dtype=torch.float32, device=x.device)
+        self.dist.all_gather_into_tensor(hn_full.view(-1), hn.reshape(-1), group=self.group)
+        q = F.linear(hn, a.to_q.weight, a.to_q.bias)
+        k = F.linear(hn_full, a.to_k.weight, a.to_k.bias)
+        v = F.linear(hn_full, a.to_v.weight, a.to_v.bias)
+        scale = 1.0 / math.sqrt(C)
+        p = torch.softmax(torch.bmm(q, k.transpose(1, 2)) * scale, dim=-1)
+        o = torch.bmm(p, v)
+        tape.append(("sattn", a, q, k, v, p, scale))
+        return x + F.linear(o, a.to_out[0].weight, a.to_out[0].bias)
+
+    def _s_attn_b(self, tape, g):
+        _, a, q, k, v, p, scale = tape.pop()
+        Tl = q.shape[1]
+        do = g @ a.to_out[0].weight
+        dv = torch.bmm(p.transpose(1, 2), do)                    # [1, T, C], partial over the query stripes
+        dp = torch.bmm(do, v.transpose(1, 2))
+        ds = torch._softmax_backward_data(dp, p, -1, p.dtype) * scale
+        dq = torch.bmm(ds, k)
+        dk = torch.bmm(ds.transpose(1, 2), q)                    # partial
+        dkv = (dk @ a.to_k.weight + dv @ a.to_v.weight).contiguous()   # project first: one reduction instead of two
+        mine = torch.empty(1, Tl, dkv.shape[2], dtype=torch.float32, device=g.device)
+        self.dist.reduce_scatter_tensor(mine.view(-1), dkv.view(-1), group=self.group)   # sum over ranks, keep my rows
+        dhn = dq @ a.to_q.weight + mine
+        return g + self._s_gn_b(tape.pop(), dhn)
+
     # ------------------------------------------------------------------ whole decoder
     def forward(self, z):
         vae, d, dist = self.vae, self.vae.decoder, self.dist
@@ -196,11 +230,11 @@ class StripedDecoderFwdBwd(DecoderFwdBwd):
             x = z.permute(0, 2, 3, 1).contiguous().view(B, H * W, -1)
             x = _conv_f(vae.post_quant_conv, x, H, W)
             x = _conv_f(d.conv_in, x, H, W)
-            x = self._resnet_f(d.mid_block.resnets[0], x, H, W, tape)         # replicated mid block
-            x = self._attn_f(d.mid_block.attentions[0], x, tape)
-            x = self._resnet_f(d.mid_block.resnets[1], x, H, W, tape)
-            rows = self.rows0
-            x = x[:, self.rank * rows * W:(self.rank + 1) * rows * W].contiguous()   # this rank's stripe
+            rows = self.rows0                                                  # conv_in (0.6 GFLOP) is replicated;
+            x = x[:, self.rank * rows * W:(self.rank + 1) * rows * W].contiguous()   # from here on: this rank's stripe
+            x = self._s_resnet_f(d.mid_block.resnets[0], x, rows, W, H * W, tape)
+            x = self._s_attn_f(d.mid_block.attentions[0], x, H * W, tape)
+            x = self._s_resnet_f(d.mid_block.resnets[1], x, rows, W, H * W, tape)
             for blk in d.up_blocks:
                 for r in blk.resnets:
                     x = self._s_resnet_f(r, x, rows, W, H * W, tape)
@@ -245,12 +279,12 @@ class StripedDecoderFwdBwd(DecoderFwdBwd):
                     g = g.view(1, rows, 2, W, 2, C).sum(dim=(2, 4)).reshape(1, rows * W, C)   # adjoint of nearest x2
                 for _ in blk.resnets:
                     g = self._s_resnet_b(tape, g)
+            g = self._s_resnet_b(tape, g)
+            g = self._s_attn_b(tape, g)
+            g = self._s_resnet_b(tape, g)
             full = torch.empty(1, H * W, g.shape[2], dtype=torch.float32, device=g.device)
             dist.all_gather_into_tensor(full.view(-1), g.contiguous().view(-1), group=self.group)
-            g = self._resnet_b(tape, full)                                     # replicated mid block
-            g = self._attn_b(tape, g)
-            g = self._resnet_b(tape, g)
-            g = self._conv_b(d.conv_in, g, d.conv_in.in_channels, H, W)
+            g = self._conv_b(d.conv_in, full, d.conv_in.in_channels, H, W)     # replicated conv_in / post_quant_conv
             g = self._conv_b(vae.post_quant_conv, g, vae.post_quant_conv.in_channels, H, W)
             self.tape = None
             out = g.view(1, H, W, -1).permute(0, 3, 1, 2).contiguous()

@@ -47,6 +47,14 @@ class _FakeDist:
         out.copy_(torch.cat([w.slots[("ag", k)].reshape(-1) for k in range(w.n)]))
         w.barrier.wait()
 
+    def reduce_scatter_tensor(self, out, inp, group=None):
+        w, r = self.w, self.w.local.rank
+        w.slots[("rs", r)] = inp.clone()
+        w.barrier.wait()
+        tot = sum(w.slots[("rs", k)] for k in range(w.n))
+        out.copy_(tot.view(w.n, -1)[r])
+        w.barrier.wait()
+
     def broadcast(self, t, src, group=None):
         w, r = self.w, self.w.local.rank
         if r == src:
