@@ -23,7 +23,13 @@ def _count(n):
     LAUNCHES += n
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """Current CUDA stream handle (raw accessor when torch exposes it: ~5x cheaper than current_stream())."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -266,11 +272,15 @@ def gather_blend_step(peer_slot_ptrs, peer_flag_ptrs, rank, slot_owner, n_region
 _gn32_ws = {}
 
 
+_gn32_ws_elems = {}
+
+
 def _gn32_workspace(x, groups):
-    lib = _lib.load()
     B, HW, C = x.shape
-    n = lib.rtti_gn32_workspace_elems(B, HW, C, groups)
-    key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+    n = _gn32_ws_elems.get((B, HW, C, groups))
+    if n is None:
+        n = _gn32_ws_elems[(B, HW, C, groups)] = _lib.load().rtti_gn32_workspace_elems(B, HW, C, groups)
+    key = (x.device.index, _stream().value)
     ws = _gn32_ws.get(key)
     if ws is None or ws.numel() < n:
         ws = torch.empty(max(n, 1 << 18), dtype=torch.float32, device=x.device)

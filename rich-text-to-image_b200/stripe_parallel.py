@@ -31,6 +31,14 @@ from . import ops
 from .vae_guidance import DecoderFwdBwd, _Tape, _cl, _conv_f, _nchw
 
 
+class _Pad:
+    """A padded conv input [rows+2, W, C] in the arena whose interior is written but whose halo exchange is pending."""
+    __slots__ = ("pad", "seq")
+
+    def __init__(self, pad, seq):
+        self.pad, self.seq = pad, seq
+
+
 class StripeArena:
     """Symmetric arena: [4 KB control block][pad half 0][pad half 1], identical layout on every rank.
 
@@ -60,6 +68,7 @@ class StripeArena:
                        self.buf[self.HEADER + self.pad_bytes:self.HEADER + 2 * self.pad_bytes]]
         self.gn_seq = 0
         self.halo_seq = 0
+        self._views = {}
 
     def next_gn_seq(self):
         self.gn_seq += 1
@@ -68,10 +77,20 @@ class StripeArena:
     def pad(self, rows, W, C):
         """Reserve the pad of the next exchange: returns (pad [rows+2, W, C] fp32 view, seq)."""
         self.halo_seq += 1
-        n = (rows + 2) * W * C * 4
-        if n > self.pad_bytes:
-            raise RuntimeError(f"stripe pad of {n} bytes exceeds the arena half ({self.pad_bytes})")
-        return self.halves[self.halo_seq & 1][:n].view(torch.float32).view(rows + 2, W, C), self.halo_seq
+        key = (self.halo_seq & 1, rows, W, C)
+        v = self._views.get(key)
+        if v is None:
+            n = (rows + 2) * W * C * 4
+            if n > self.pad_bytes:
+                raise RuntimeError(f"stripe pad of {n} bytes exceeds the arena half ({self.pad_bytes})")
+            v = self._views[key] = self.halves[key[0]][:n].view(torch.float32).view(rows + 2, W, C)
+        return v, self.halo_seq
+
+    def release(self, seq):
+        """Give back the most recent pad() without exchanging it (its interior was only used as plain memory), so
+        that exchanged pads keep alternating between the two halves."""
+        assert seq == self.halo_seq
+        self.halo_seq -= 1
 
     def exchange(self, pad, seq):
         assert seq == self.halo_seq, "pad()/exchange() must pair up in order"
@@ -152,12 +171,25 @@ class StripedDecoderFwdBwd(DecoderFwdBwd):
             self._wflip[k] = conv.weight.flip(2, 3).transpose(0, 1).contiguous(memory_format=torch.channels_last)
         return self._wflip[k]
 
+    def _new_pad(self, rows, W, C):
+        """Pad of the NEXT exchange, to be filled by a producer kernel: (_Pad, interior view [1, rows*W, C])."""
+        pad, seq = self.arena.pad(rows, W, C)
+        return _Pad(pad, seq), pad[1:-1].view(1, rows * W, C)
+
+    @staticmethod
+    def _renew_pad(gp, rows, W, C):
+        """Re-use a pad whose exchange has not happened yet (its interior is about to be overwritten)."""
+        return gp, gp.pad[1:-1].view(1, rows * W, C)
+
     def _s_conv3_b(self, conv, g, rows, W):
-        """d/d input of a striped 3x3 convolution; g [1, rows*W, Cout] is copied into a pad and haloed."""
-        pad, seq = self.arena.pad(rows, W, g.shape[2])
-        pad[1:-1].view(-1).copy_(g.reshape(-1))
-        self.arena.exchange(pad, seq)
-        return self._conv_pad(self._flipped(conv), None, pad)
+        """d/d input of a striped 3x3 convolution. g: a _Pad whose interior already holds the output gradient
+        (written there by its producer), or a plain [1, rows*W, Cout] tensor that is copied into a fresh pad."""
+        if not isinstance(g, _Pad):
+            gp, interior = self._new_pad(rows, W, g.shape[2])
+            interior.copy_(g.view_as(interior))
+            g = gp
+        self.arena.exchange(g.pad, g.seq)
+        return self._conv_pad(self._flipped(conv), None, g.pad)
 
     def _s_resnet_f(self, r, x, rows, W, hw_total, tape):
         cin, cout = r.conv1.in_channels, r.conv1.out_channels
@@ -174,17 +206,24 @@ class StripedDecoderFwdBwd(DecoderFwdBwd):
         return ops.add_bias_f32(sc, h, r.conv2.bias)
 
     def _s_resnet_b(self, tape, g):
+        """g: _Pad (un-exchanged, interior = gradient of the block output). Returns a _Pad holding the gradient of
+        the block input, again un-exchanged, so the consumer (the next resnet / upsampler gradient) needs no staging
+        copy. Hazard rule for pads (two halves, alternating): anything that reads pad s other than its convolution
+        must run before this rank pushes exchange s+1 — unless it reads only the interior and pad s+2 has the same
+        shape (neighbours only ever write halo rows). Hence the 1x1 shortcut gradient is taken first, and the
+        identity-shortcut add runs in place."""
         _, r, rows, W = tape.pop()
         cin, cout = r.conv1.in_channels, r.conv1.out_channels
+        g_int = g.pad[1:-1].view(1, rows * W, cout)
+        sc = self._conv_b(r.conv_shortcut, g_int, cin, rows, W) if r.conv_shortcut is not None else None
         dh = self._s_conv3_b(r.conv2, g, rows, W)
-        pad, seq = self.arena.pad(rows, W, cout)
-        self._s_gn_b(tape.pop(), dh, out=pad[1:-1].view(1, rows * W, cout))   # straight into the next conv's pad
-        self.arena.exchange(pad, seq)
-        dh = self._conv_pad(self._flipped(r.conv1), None, pad)
+        p2, p2_int = self._new_pad(rows, W, cout)
+        self._s_gn_b(tape.pop(), dh, out=p2_int)                    # straight into the next conv's pad
+        dh = self._s_conv3_b(r.conv1, p2, rows, W)
         dx = self._s_gn_b(tape.pop(), dh)
-        if r.conv_shortcut is not None:
-            return ops.add_bias_f32(dx, self._conv_b(r.conv_shortcut, g, cin, rows, W))
-        return ops.add_bias_f32(dx, g.contiguous())
+        out, out_int = self._new_pad(rows, W, cin)                  # same half as g (two exchanges later)
+        ops.add_bias_f32(dx, sc if sc is not None else g_int, out=out_int)   # identity case: in place over g
+        return out
 
     def _s_attn_f(self, a, x, hw_total, tape):
         """Mid-block attention with this rank's stripe of queries against all keys/values: GroupNorm striped, the
@@ -270,20 +309,27 @@ class StripedDecoderFwdBwd(DecoderFwdBwd):
             r0 = self.rank * rows
             g = grad_image[:, :, r0:r0 + rows, :].permute(0, 2, 3, 1).contiguous().view(1, rows * W, -1)
             g = self._s_conv3_b(d.conv_out, g, rows, W)
-            g = self._s_gn_b(tape.pop(), g)
+            gp, g_int = self._new_pad(rows, W, g.shape[2])
+            self._s_gn_b(tape.pop(), g, out=g_int)
             for blk in reversed(d.up_blocks):
                 if blk.upsamplers is not None:
                     _, conv, rows, W, C = tape.pop()
-                    g = self._s_conv3_b(conv, g, rows, W)
+                    g = self._s_conv3_b(conv, gp, rows, W)
                     rows, W, H = rows // 2, W // 2, H // 2
-                    g = g.view(1, rows, 2, W, 2, C).sum(dim=(2, 4)).reshape(1, rows * W, C)   # adjoint of nearest x2
+                    gp, g_int = self._new_pad(rows, W, C)
+                    torch.sum(g.view(1, rows, 2, W, 2, C), dim=(2, 4), out=g_int.view(1, rows, W, C))   # adjoint of nearest x2
                 for _ in blk.resnets:
-                    g = self._s_resnet_b(tape, g)
-            g = self._s_resnet_b(tape, g)
-            g = self._s_attn_b(tape, g)
-            g = self._s_resnet_b(tape, g)
+                    gp = self._s_resnet_b(tape, gp)
+            gp = self._s_resnet_b(tape, gp)
+            C = gp.pad.shape[2]
+            g = self._s_attn_b(tape, gp.pad[1:-1].view(1, rows * W, C))   # reads the interior only; result is a new tensor
+            gp, g_int = self._renew_pad(gp, rows, W, C)
+            g_int.copy_(g)
+            gp = self._s_resnet_b(tape, gp)
+            g = gp.pad[1:-1].view(1, rows * W, -1)
             full = torch.empty(1, H * W, g.shape[2], dtype=torch.float32, device=g.device)
-            dist.all_gather_into_tensor(full.view(-1), g.contiguous().view(-1), group=self.group)
+            dist.all_gather_into_tensor(full.view(-1), g.reshape(-1), group=self.group)
+            self.arena.release(gp.seq)
             g = self._conv_b(d.conv_in, full, d.conv_in.in_channels, H, W)     # replicated conv_in / post_quant_conv
             g = self._conv_b(vae.post_quant_conv, g, vae.post_quant_conv.in_channels, H, W)
             self.tape = None

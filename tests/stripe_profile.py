@@ -16,7 +16,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = os.environ.get("RTTI_CUDNN_BENCHMARK", "1") == "1"
     from rtti_b200.stripe_parallel import StripedDecoderFwdBwd
     from rtti_b200.vae import AutoencoderKLDecoder, VAEConfig
     vae = AutoencoderKLDecoder(VAEConfig.sdxl()).init_synthetic(seed=5).finalize("cuda")
@@ -44,7 +44,22 @@ def main():
         eng.backward(grad_fn(eng.forward(z)))
         torch.cuda.synchronize()
     eng.arena.check()
-    if rank == 0:
+    # per-rank totals of the kernels that matter for the skew analysis (every rank profiles itself)
+    tot = {}
+    for e in prof.key_averages():
+        t = getattr(e, "self_device_time_total", None)
+        if t is None:
+            t = e.self_cuda_time_total
+        for key in ("gn32_finalize_peer_kernel<0>", "gn32_finalize_peer_kernel<1>", "halo_exchange", "implicit_gemm", "conv3d_fprop",
+                    "gn32_partial", "gn32_apply", "ncclDevKernel"):
+            if key in e.key:
+                tot[key] = tot.get(key, 0.0) + t / 1e3
+    for r in range(world):
+        if r == rank:
+            print(f"rank {rank} (cudnn.benchmark={torch.backends.cudnn.benchmark}) kernel ms: " +
+                  ", ".join(f"{k}={v:.2f}" for k, v in sorted(tot.items())), flush=True)
+        dist.barrier()
+    if rank == 0 and os.environ.get("RTTI_PROFILE_TABLE", "0") == "1":
         print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70), flush=True)
     dist.barrier()
     dist.destroy_process_group()

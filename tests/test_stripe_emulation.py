@@ -84,6 +84,10 @@ class _FakeArena:
         assert n * 4 <= self.pad_bytes
         return self.halves[self.halo_seq & 1][:n].view(rows + 2, W, C), self.halo_seq
 
+    def release(self, seq):
+        assert seq == self.halo_seq
+        self.halo_seq -= 1
+
     def exchange(self, pad, seq):
         assert seq == self.halo_seq
         w, r = self.w, self.rank
