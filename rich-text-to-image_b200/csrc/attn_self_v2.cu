@@ -12,6 +12,8 @@
 //   * P_j overwrites its own S buffer as packed fp16 and feeds the PV MMA from TMEM (TS operand);
 //   * the lazy O rescale (rare) waits for PV_{j-1} on its own barrier, because QK^T_{j} no longer implies it.
 // Warps: 0-7 softmax/epilogue, 8 TMA producer, 9 MMA issuer + TMEM owner. 3-stage K/V ring.
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "rtti_internal.h"
 
@@ -43,7 +45,7 @@ constexpr int THREADS = 320;
 __global__ void __launch_bounds__(v2::THREADS, 1)
 attn_self_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
-                    const AttnV2Params p) {
+                    const __grid_constant__ AttnV2Params p) {
   using namespace v2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -270,6 +272,7 @@ int launch_attn_self_v2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
 // warp on a sub-partition loads S / takes the max / stores P, the other CTA's warp keeps the MUFU pipe busy.
 // TMEM per CTA: S0 [0,64), S1 [64,128), O [128,192) -> 256-column allocation, two CTAs fill the 512 columns.
 namespace rtti {
+constexpr int V3_POLY_DEFAULT = 0;
 namespace v3 {
 constexpr int KT = 64;
 constexpr int NSTAGE = 4;
@@ -283,12 +286,29 @@ constexpr int OFF_BAR = OFF_O + Q_TILE;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // ~98 KB -> 2 CTAs / SM
 constexpr uint32_t O_COL = 128;
 constexpr int THREADS = 192;
+
+// 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic
+// minimax polynomial for 2^f (max relative error 7.5e-5 = 2^-13.7, six times below the fp16 rounding of P), and
+// n added into the exponent field. Inputs below -126 (masked keys: -inf) are clamped -> 2^-126, which is 0 in fp16.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;                 // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.f);
+  float pl = fmaf(0.0551716685f, f, 0.2426111251f);
+  pl = fmaf(pl, f, 0.6932609677f);
+  pl = fmaf(pl, f, 0.9999280572f);
+  return __uint_as_float(__float_as_uint(pl) + (__float_as_uint(t) << 23));
+}
 }  // namespace v3
 
+// POLY: every POLY-th exponential of a row is evaluated with v3::exp2_poly instead of ex2.approx (0 = none). The
+// softmax warps are bound by the 16-lane/SM MUFU pipe; moving a fraction of the exponentials to the FMA pipe
+// (FlashAttention-4's trick) shortens the MUFU burst of every tile.
+template <int POLY>
 __global__ void __launch_bounds__(v3::THREADS, 2)
 attn_self_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
-                    const AttnV2Params p) {
+                    const __grid_constant__ AttnV2Params p) {
   using namespace v3;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -422,8 +442,10 @@ attn_self_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float e0 = ex2_approx(fmaf(s[2 * i], p.scale_log2, -m_ref));
-        const float e1 = ex2_approx(fmaf(s[2 * i + 1], p.scale_log2, -m_ref));
+        const float x0 = fmaf(s[2 * i], p.scale_log2, -m_ref);
+        const float x1 = fmaf(s[2 * i + 1], p.scale_log2, -m_ref);
+        const float e0 = (POLY > 0 && (2 * i) % POLY == POLY - 1) ? exp2_poly(x0) : ex2_approx(x0);
+        const float e1 = (POLY > 0 && (2 * i + 1) % POLY == POLY - 1) ? exp2_poly(x1) : ex2_approx(x1);
         rowsum += e0 + e1;
         pk[i] = pack_half2(e0, e1);
       }
@@ -472,10 +494,17 @@ attn_self_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 int launch_attn_self_v3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                         int batch, int heads, int head_dim, int n_q, int n_k, float scale_log2, const int8_t* qk_src,
                         float* lse, cudaStream_t stream) {
+  // RTTI_ATTN_POLY = 0 | 2 | 3 | 4 | 8: fraction 1/k of the exponentials on the FMA pipe (read once at first launch)
+  static const int poly = [] { const char* e = getenv("RTTI_ATTN_POLY"); return e ? atoi(e) : V3_POLY_DEFAULT; }();
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_self_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) != cudaSuccess)
-      return RTTI_ERR_CUDA;
+    bool ok = true;
+    ok &= cudaFuncSetAttribute(attn_self_v3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_self_v3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_self_v3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_self_v3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_self_v3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) == cudaSuccess;
+    if (!ok) return RTTI_ERR_CUDA;
     configured = true;
   }
   AttnV2Params p{};
@@ -486,7 +515,13 @@ int launch_attn_self_v3(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
   for (int i = 0; i < 64; ++i) p.qk_src[i] = qk_src[i];
   p.lse = lse;
   dim3 grid((n_q + 127) / 128, heads, batch);
-  attn_self_v3_kernel<<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  switch (poly) {
+    case 2: attn_self_v3_kernel<2><<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p); break;
+    case 3: attn_self_v3_kernel<3><<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p); break;
+    case 4: attn_self_v3_kernel<4><<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p); break;
+    case 8: attn_self_v3_kernel<8><<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p); break;
+    default: attn_self_v3_kernel<0><<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p); break;
+  }
   return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
 }
 }  // namespace rtti

@@ -203,7 +203,29 @@ CASES = {
     "v1:d40": lambda: attn_case(2, 8, 40, 256, 256),
     # 64-key-tile / 3 CTAs per SM experiment: RTTI_ATTN_KT64=1
     "kt64:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    # v3 with 1/4 resp. 1/2 of the exponentials evaluated by the FMA-pipe polynomial: RTTI_ATTN_POLY=4 / 2
+    "poly4:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    "poly4:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
+    "poly4:d40": lambda: attn_case(2, 8, 40, 256, 256),
+    "poly2:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    "poly0:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
 }
+
+
+def case_env(name):
+    """Environment of the subprocess that runs case `name` (the prefix selects an attention schedule switch)."""
+    env = dict(os.environ)
+    if name.startswith("exp16:"):
+        env["RTTI_ATTN_EXP16"] = "1"; env["RTTI_ATTN_V1"] = "1"
+    if name.startswith("kt64:"):
+        env["RTTI_ATTN_KT64"] = "1"; env["RTTI_ATTN_V1"] = "1"
+    if name.startswith("v1:"):
+        env["RTTI_ATTN_V1"] = "1"
+    if name.startswith("v2:"):
+        env["RTTI_ATTN_V2"] = "1"
+    if name.startswith("poly"):
+        env["RTTI_ATTN_POLY"] = name[4:name.index(":")]
+    return env
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
@@ -212,15 +234,7 @@ if __name__ == "__main__":
     summary = []
     for name in CASES:
         try:
-            env = dict(os.environ)
-            if name.startswith("exp16:"):
-                env["RTTI_ATTN_EXP16"] = "1"; env["RTTI_ATTN_V1"] = "1"
-            if name.startswith("kt64:"):
-                env["RTTI_ATTN_KT64"] = "1"; env["RTTI_ATTN_V1"] = "1"
-            if name.startswith("v1:"):
-                env["RTTI_ATTN_V1"] = "1"
-            if name.startswith("v2:"):
-                env["RTTI_ATTN_V2"] = "1"
+            env = case_env(name)
             r = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=120, capture_output=True, text=True, env=env)
             out = (r.stdout + r.stderr).strip()
             status = "ok" if r.returncode == 0 else f"rc={r.returncode}"

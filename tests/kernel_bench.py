@@ -66,6 +66,8 @@ def main():
         report(f"attn_fwd self {tag} B{B} h{H} T{T}", sec, nbytes=2 * 4 * B * T * C, flops=4.0 * B * H * T * T * 64, bound="tensor")
         sec = timeit(lambda: ops.attention(q, k, v, H, out=o, qk_src=[0, 1, 2, 3, 3, 3, 3, 3]))
         report(f"attn_fwd self+inject {tag}", sec, flops=4.0 * B * H * T * T * 64, bound="tensor")
+        if os.environ.get("RTTI_KBENCH_ONLY") == "self":   # A/B runs of the self-attention schedule switches
+            continue
         kc, vc = rn(B, 77, C), rn(B, 77, C)
         qc = rn(B, T, C)
         sec = timeit(lambda: ops.attention(qc, kc, vc, H, out=o))
@@ -82,6 +84,8 @@ def main():
             acc = torch.zeros(T, T, device="cuda")
             sec = timeit(lambda: ops.attn_probs_mean_accum(q[1], k[1], lse[1], acc, H))
             report(f"attn_probs_mean {tag}", sec, nbytes=8 * T * T + 4 * T * C, flops=2.0 * H * T * T * 64, bound="tensor")
+    if os.environ.get("RTTI_KBENCH_ONLY") == "self":
+        return
     for (HW, C) in ((16384, 320), (4096, 640), (4096, 1920), (1024, 1280), (1024, 2560)):
         x = rn(B, HW, C); ga, be = rn(C), rn(C); y = torch.empty_like(x); tb = rn(B, C)
         sec = timeit(lambda: ops.groupnorm_silu(x, ga, be, 32, 1e-5, True, chan_bias=tb, out=y))

@@ -15,16 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.parametrize("case", list(gpu_diag.CASES))
 def test_kernel_case(case):
-    env = dict(os.environ)
-    if case.startswith("exp16:"):
-        env["RTTI_ATTN_EXP16"] = "1"; env["RTTI_ATTN_V1"] = "1"
-    if case.startswith("kt64:"):
-        env["RTTI_ATTN_KT64"] = "1"; env["RTTI_ATTN_V1"] = "1"
-    if case.startswith("v1:"):
-        env["RTTI_ATTN_V1"] = "1"
-    if case.startswith("v2:"):
-        env["RTTI_ATTN_V2"] = "1"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gpu_diag.py"), case], capture_output=True, text=True,
-                       timeout=300, env=env)
+                       timeout=300, env=gpu_diag.case_env(case))
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "FAIL" not in r.stdout
