@@ -292,7 +292,11 @@ def run_product(args, rank, world, local_rank):
         if s:
             ach = s[1] / s[0] / 1e12
             roof = {"kernel": "attn_self_v3_kernel (self-attention, tcgen05/TMEM, head_dim 64)", "bound": "tensor", "achieved": ach,
-                    "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust, "traffic": None,
+                    "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust, "traffic": 68.73e6,
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum = 62.95 + 5.77 MB for one launch of the "
+                                    "32x32-level shape (B8 h20 T1024 d64: 60 of the 70 launches of a step; algorithmic Q+K+V+O "
+                                    "= 83.9 MB, part of O still in L2 at kernel end), ncu --set full capture "
+                                    "profiles/r01_attn_self_v3_ncu_details.txt",
                     "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                     "launches_timed": s[3], "ms_per_step_in_kernel": s[0] * 1e3}
         if c:

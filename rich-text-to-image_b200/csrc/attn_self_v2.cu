@@ -273,6 +273,8 @@ int launch_attn_self_v2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
 // TMEM per CTA: S0 [0,64), S1 [64,128), O [128,192) -> 256-column allocation, two CTAs fill the 512 columns.
 namespace rtti {
 constexpr int V3_POLY_DEFAULT = 0;
+constexpr bool V3_ILP_DEFAULT = false;
+constexpr bool V3_PF_DEFAULT = false;
 namespace v3 {
 constexpr int KT = 64;
 constexpr int NSTAGE = 4;
@@ -304,7 +306,12 @@ __device__ __forceinline__ float exp2_poly(float x) {
 // POLY: every POLY-th exponential of a row is evaluated with v3::exp2_poly instead of ex2.approx (0 = none). The
 // softmax warps are bound by the 16-lane/SM MUFU pipe; moving a fraction of the exponentials to the FMA pipe
 // (FlashAttention-4's trick) shortens the MUFU burst of every tile.
-template <int POLY>
+// ILP: row max and row sum are reduced as four independent chains (the straight loops compile to 31-deep FMNMX3 and
+// 32-deep FADD dependency chains; a softmax warp is latency-bound, not throughput-bound — see DESIGN.md §3.1).
+// PF: software-pipelined softmax — the TMEM load of S_{j+1} is issued before the exponentials of tile j and lands
+// half-way through them, and its row max is computed in the same basic block as the second half of the exponentials,
+// so the load latency and the max chain of the next tile hide under the MUFU work of the current one.
+template <int POLY, bool ILP, bool PF>
 __global__ void __launch_bounds__(v3::THREADS, 2)
 attn_self_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
@@ -398,62 +405,162 @@ attn_self_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const bool row_ok = (q0 + row) < p.n_q;
     float m_ref = -INFINITY, l = 0.f;
-    for (int j = 0; j < nt; ++j) {
-      const uint32_t s_col = 64u * (j & 1);
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      float s[64];
-      tmem_ld32(tlane + s_col, reinterpret_cast<uint32_t*>(s));
-      tmem_ld32(tlane + s_col + 32, reinterpret_cast<uint32_t*>(s) + 32);
-      tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s));
-      tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s) + 32);
-      const int valid = p.n_k - j * KT;
-      if (valid < KT) {
+    if constexpr (PF) {
+      float sA[64], sB[64];
+      auto row_max = [&](const float (&s)[64]) {
+        float m4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-        for (int i = 0; i < KT; ++i)
-          if (i >= valid) s[i] = -INFINITY;
-      }
-      float mx = s[0];
+        for (int i = 4; i < KT; i += 4) {
 #pragma unroll
-      for (int i = 1; i < KT; ++i) mx = fmaxf(mx, s[i]);
-      const float mxs = mx * p.scale_log2;
-      if (j == 0) {
-        m_ref = mxs;
-      } else {
-        const bool need = mxs > m_ref + 8.f;
-        if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(pv_done, (j - 1) & 1);   // O is being accumulated by PV_{j-1}
-          tc_fence_after();
-          const float alpha = need ? ex2_approx(m_ref - mxs) : 1.f;
-          if (need) m_ref = mxs;
-          l *= alpha;
+          for (int c = 0; c < 4; ++c) m4[c] = fmaxf(m4[c], s[i + c]);
+        }
+        return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      };
+      auto load = [&](int j, float (&s)[64]) {          // asynchronous: the registers are not valid until land()
+        mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        tmem_ld32(tlane + 64u * (j & 1), reinterpret_cast<uint32_t*>(s));
+        tmem_ld32(tlane + 64u * (j & 1) + 32, reinterpret_cast<uint32_t*>(s) + 32);
+      };
+      auto land = [&](int j, float (&s)[64]) {
+        tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s));
+        tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s) + 32);
+        const int valid = p.n_k - j * KT;
+        if (valid < KT) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[16];
-            tmem_ld16(tlane + O_COL + 16 * c, o);
-            tmem_wait_ld_regs16(o);
+          for (int i = 0; i < KT; ++i)
+            if (i >= valid) s[i] = -INFINITY;
+        }
+      };
+      auto tile = [&](int j, float (&cur)[64], float (&nxt)[64], float mx) -> float {
+        const uint32_t s_col = 64u * (j & 1);
+        const float mxs = mx * p.scale_log2;
+        if (j == 0) {
+          m_ref = mxs;
+        } else {
+          const bool need = mxs > m_ref + 8.f;
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(pv_done, (j - 1) & 1);   // O is being accumulated by PV_{j-1}
+            tc_fence_after();
+            const float alpha = need ? ex2_approx(m_ref - mxs) : 1.f;
+            if (need) m_ref = mxs;
+            l *= alpha;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tlane + O_COL + 16 * c, o);
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[16];
+              tmem_ld16(tlane + O_COL + 16 * c, o);
+              tmem_wait_ld_regs16(o);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tlane + O_COL + 16 * c, o);
+            }
           }
         }
-      }
-      float rowsum = 0.f;
-      uint32_t pk[32];
+        const bool has_next = j + 1 < nt;
+        if (has_next) load(j + 1, nxt);
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float x0 = fmaf(s[2 * i], p.scale_log2, -m_ref);
-        const float x1 = fmaf(s[2 * i + 1], p.scale_log2, -m_ref);
-        const float e0 = (POLY > 0 && (2 * i) % POLY == POLY - 1) ? exp2_poly(x0) : ex2_approx(x0);
-        const float e1 = (POLY > 0 && (2 * i + 1) % POLY == POLY - 1) ? exp2_poly(x1) : ex2_approx(x1);
-        rowsum += e0 + e1;
-        pk[i] = pack_half2(e0, e1);
+        for (int i = 0; i < 16; ++i) {
+          const float e0 = ex2_approx(fmaf(cur[2 * i], p.scale_log2, -m_ref));
+          const float e1 = ex2_approx(fmaf(cur[2 * i + 1], p.scale_log2, -m_ref));
+          rs4[i & 3] += e0 + e1;
+          pk[i] = pack_half2(e0, e1);
+        }
+        if (has_next) land(j + 1, nxt);
+        const float mx_next = row_max(nxt);    // unconditional: same basic block as the exponentials below (unused if !has_next)
+#pragma unroll
+        for (int i = 16; i < 32; ++i) {
+          const float e0 = ex2_approx(fmaf(cur[2 * i], p.scale_log2, -m_ref));
+          const float e1 = ex2_approx(fmaf(cur[2 * i + 1], p.scale_log2, -m_ref));
+          rs4[i & 3] += e0 + e1;
+          pk[i] = pack_half2(e0, e1);
+        }
+        l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+        tmem_st32(tlane + s_col, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[j & 1]);
+        return mx_next;
+      };
+#pragma unroll
+      for (int i = 0; i < 64; ++i) sB[i] = 0.f;
+      load(0, sA);
+      land(0, sA);
+      float mx = row_max(sA);
+      for (int j = 0; j < nt; j += 2) {
+        mx = tile(j, sA, sB, mx);
+        if (j + 1 < nt) mx = tile(j + 1, sB, sA, mx);
       }
-      l += rowsum;
-      tmem_st32(tlane + s_col, pk);          // packed P_j over the first 32 columns of its own S buffer
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_full[j & 1]);
+    } else {
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t s_col = 64u * (j & 1);
+        mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        float s[64];
+        tmem_ld32(tlane + s_col, reinterpret_cast<uint32_t*>(s));
+        tmem_ld32(tlane + s_col + 32, reinterpret_cast<uint32_t*>(s) + 32);
+        tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s));
+        tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s) + 32);
+        const int valid = p.n_k - j * KT;
+        if (valid < KT) {
+  #pragma unroll
+          for (int i = 0; i < KT; ++i)
+            if (i >= valid) s[i] = -INFINITY;
+        }
+        float mx;
+        if (ILP) {
+          float m4[4] = {s[0], s[1], s[2], s[3]};
+  #pragma unroll
+          for (int i = 4; i < KT; i += 4) {
+  #pragma unroll
+            for (int c = 0; c < 4; ++c) m4[c] = fmaxf(m4[c], s[i + c]);
+          }
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        } else {
+          mx = s[0];
+  #pragma unroll
+          for (int i = 1; i < KT; ++i) mx = fmaxf(mx, s[i]);
+        }
+        const float mxs = mx * p.scale_log2;
+        if (j == 0) {
+          m_ref = mxs;
+        } else {
+          const bool need = mxs > m_ref + 8.f;
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(pv_done, (j - 1) & 1);   // O is being accumulated by PV_{j-1}
+            tc_fence_after();
+            const float alpha = need ? ex2_approx(m_ref - mxs) : 1.f;
+            if (need) m_ref = mxs;
+            l *= alpha;
+  #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[16];
+              tmem_ld16(tlane + O_COL + 16 * c, o);
+              tmem_wait_ld_regs16(o);
+  #pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tlane + O_COL + 16 * c, o);
+            }
+          }
+        }
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[32];
+  #pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x0 = fmaf(s[2 * i], p.scale_log2, -m_ref);
+          const float x1 = fmaf(s[2 * i + 1], p.scale_log2, -m_ref);
+          const float e0 = (POLY > 0 && (2 * i) % POLY == POLY - 1) ? exp2_poly(x0) : ex2_approx(x0);
+          const float e1 = (POLY > 0 && (2 * i + 1) % POLY == POLY - 1) ? exp2_poly(x1) : ex2_approx(x1);
+          rs4[ILP ? (i & 3) : 0] += e0 + e1;
+          pk[i] = pack_half2(e0, e1);
+        }
+        l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+        tmem_st32(tlane + s_col, pk);          // packed P_j over the first 32 columns of its own S buffer
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[j & 1]);
+      }
     }
     mbar_wait(o_full, 0);
     tc_fence_after();
@@ -494,19 +601,21 @@ attn_self_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 int launch_attn_self_v3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                         int batch, int heads, int head_dim, int n_q, int n_k, float scale_log2, const int8_t* qk_src,
                         float* lse, cudaStream_t stream) {
-  // RTTI_ATTN_POLY = 0 | 2 | 3 | 4 | 8: fraction 1/k of the exponentials on the FMA pipe (read once at first launch)
+  // RTTI_ATTN_POLY = 0 | 4 | 8: fraction 1/k of the exponentials on the FMA pipe; RTTI_ATTN_ILP / RTTI_ATTN_PF = 0 | 1 (read once)
   static const int poly = [] { const char* e = getenv("RTTI_ATTN_POLY"); return e ? atoi(e) : V3_POLY_DEFAULT; }();
-  static bool configured = false;
-  if (!configured) {
-    bool ok = true;
-    ok &= cudaFuncSetAttribute(attn_self_v3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_self_v3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_self_v3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_self_v3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_self_v3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) == cudaSuccess;
-    if (!ok) return RTTI_ERR_CUDA;
-    configured = true;
-  }
+  static const bool ilp = [] { const char* e = getenv("RTTI_ATTN_ILP"); return e ? atoi(e) != 0 : V3_ILP_DEFAULT; }();
+  using KernelT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnV2Params);
+  static const bool pf = [] { const char* e = getenv("RTTI_ATTN_PF"); return e ? atoi(e) != 0 : V3_PF_DEFAULT; }();
+  static const KernelT kernel = [] {
+    KernelT k = ilp ? attn_self_v3_kernel<0, true, false> : attn_self_v3_kernel<0, false, false>;
+    if (poly == 4) k = ilp ? attn_self_v3_kernel<4, true, false> : attn_self_v3_kernel<4, false, false>;
+    if (poly == 8) k = ilp ? attn_self_v3_kernel<8, true, false> : attn_self_v3_kernel<8, false, false>;
+    if (pf) k = attn_self_v3_kernel<0, true, true>;
+    return k;
+  }();
+  static const bool configured =
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES) == cudaSuccess;
+  if (!configured) return RTTI_ERR_CUDA;
   AttnV2Params p{};
   p.batch = batch; p.heads = heads; p.head_dim = head_dim; p.n_q = n_q; p.n_k = n_k;
   p.n_k_tiles = (n_k + v3::KT - 1) / v3::KT;
@@ -515,13 +624,7 @@ int launch_attn_self_v3(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
   for (int i = 0; i < 64; ++i) p.qk_src[i] = qk_src[i];
   p.lse = lse;
   dim3 grid((n_q + 127) / 128, heads, batch);
-  switch (poly) {
-    case 2: attn_self_v3_kernel<2><<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p); break;
-    case 3: attn_self_v3_kernel<3><<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p); break;
-    case 4: attn_self_v3_kernel<4><<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p); break;
-    case 8: attn_self_v3_kernel<8><<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p); break;
-    default: attn_self_v3_kernel<0><<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p); break;
-  }
+  kernel<<<grid, v3::THREADS, v3::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
   return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
 }
 }  // namespace rtti

@@ -207,8 +207,18 @@ CASES = {
     "poly4:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
     "poly4:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
     "poly4:d40": lambda: attn_case(2, 8, 40, 256, 256),
-    "poly2:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    "poly0:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    "poly8:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    # v3 with four independent max / sum chains: RTTI_ATTN_ILP=1
+    "ilp:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    "ilp:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
+    # v3 software-pipelined softmax (S_{j+1} prefetched under the exponentials of tile j): RTTI_ATTN_PF=1
+    "pf:self_1tile": lambda: attn_case(1, 1, 64, 128, 128),
+    "pf:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    "pf:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
+    "pf:self_inject": lambda: attn_case(4, 2, 64, 256, 256, qk_src=[0, 1, 1, 1]),
+    "pf:d40": lambda: attn_case(2, 8, 40, 256, 256),
+    "pf:self_4096": lambda: attn_case(1, 10, 64, 4096, 4096, fused_qkv=True),
+    "pf:odd_tiles": lambda: attn_case(2, 2, 64, 320, 320, want_lse=True),
 }
 
 
@@ -225,6 +235,10 @@ def case_env(name):
         env["RTTI_ATTN_V2"] = "1"
     if name.startswith("poly"):
         env["RTTI_ATTN_POLY"] = name[4:name.index(":")]
+    if name.startswith("ilp:"):
+        env["RTTI_ATTN_ILP"] = "1"
+    if name.startswith("pf:"):
+        env["RTTI_ATTN_PF"] = "1"
     return env
 
 if __name__ == "__main__":
