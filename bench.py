@@ -33,6 +33,14 @@ WORKLOAD = ("SDXL 1024x1024 font-color example shape: 5 region prompts, color_gu
             "inject_background=0.5, 8 UNet passes/step, 41-step Euler schedule")
 
 
+def bench_config():
+    """`config` of the JSON line: identical for the product arm and the --impl reference arm."""
+    return {"workload": WORKLOAD, "passes_per_step": PASSES_PER_STEP,
+            "unet_tflop_per_step": PASSES_PER_STEP * UNET_PASS_GFLOP / 1e3,
+            "l2": "inputs larger than L2: 5.1 GB of fp16 UNet weights stream every step",
+            "vae": "SDXL AutoencoderKL decoder, random weights, fp32/TF32, fwd+bwd inside the step"}
+
+
 def synth_workload(device):
     import torch
     g = torch.Generator().manual_seed(7)
@@ -174,7 +182,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "denoising steps/sec SDXL 1024^2 5-region", "value": v, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD},
+        "config": bench_config(),
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -312,11 +320,10 @@ def run_product(args, rank, world, local_rank):
         "metric": "denoising steps/sec SDXL 1024^2 5-region", "value": steps_per_s, "unit": "steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "execution": "the 8 passes run as one batched, CUDA-graph-replayed UNet call",
-                   "l2": "inputs larger than L2: 5.1 GB of fp16 UNet weights stream every step",
-                   "parallelism": f"region-parallel x{world}" if world > 1 else "single GPU",
-                   "unet_tflop_per_step": PASSES_PER_STEP * UNET_PASS_GFLOP / 1e3,
-                   "vae": "SDXL AutoencoderKL decoder, random weights, fp32/TF32, fwd+bwd inside the step"},
+        "config": bench_config(),
+        "execution": "the passes of a rank run as one batched, CUDA-graph-replayed UNet call",
+        "parallelism": (f"UNet passes region-parallel x{world} (fused peer-memory exchange), colour guidance stripe-parallel x{world}"
+                        if world > 1 else "single GPU"),
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": args.steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "last_color_loss": loss},
