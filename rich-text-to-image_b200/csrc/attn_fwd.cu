@@ -525,6 +525,8 @@ static const bool g_exp16 = [] { const char* e = getenv("RTTI_ATTN_EXP16"); retu
 static const bool g_v2 = [] { const char* e = getenv("RTTI_ATTN_V1"); return !(e && e[0] == '1'); }();
 // RTTI_ATTN_V2=1 selects the 1-CTA/SM, 2-threads-per-row schedule (v2) instead of v3 for head_dim <= 64.
 static const bool g_v3 = [] { const char* e = getenv("RTTI_ATTN_V2"); return !(e && e[0] == '1'); }();
+// RTTI_ATTN_V4=1: experimental triple-buffered / quarter-pipelined schedule (attn_self_v4.cu), same operands as v3.
+static const bool g_v4 = [] { const char* e = getenv("RTTI_ATTN_V4"); return e && e[0] == '1'; }();
 static const bool g_use_kt64 = [] { const char* e = getenv("RTTI_ATTN_KT64"); return e && e[0] == '1'; }();
 
 extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads,
@@ -597,8 +599,10 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
     if (ndch == 2) RTTI_LAUNCH(80, 2, false);
     RTTI_LAUNCH(80, 3, false);
   }
-  if (use_v3)   // 64-key tiles, MMA look-ahead, one thread per row, 2 CTAs/SM (attn_self_v2.cu)
+  if (use_v3) {   // 64-key tiles, MMA look-ahead, one thread per row, 2 CTAs/SM (attn_self_v2.cu)
+    if (g_v4) return launch_attn_self_v4(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.qk_src, lse, st);
     return launch_attn_self_v3(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.qk_src, lse, st);
+  }
   if (KT == 64) RTTI_LAUNCH(64, 1, false);
   if (ndch == 1 && g_v2 && !g_exp16)   // software-pipelined kernel (attn_self_v2.cu): 1 CTA/SM, MMAs hidden behind exps
     return launch_attn_self_v2(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.qk_src, lse, st);

@@ -27,6 +27,11 @@ int launch_attn_self_v3(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
                         int batch, int heads, int head_dim, int n_q, int n_k, float scale_log2, const int8_t* qk_src,
                         float* lse, cudaStream_t stream);
 
+// attn_self_v4.cu: EXPERIMENTAL (RTTI_ATTN_V4=1 only) — three S buffers, quarter-tile software pipeline; same maps as v3
+int launch_attn_self_v4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                        int batch, int heads, int head_dim, int n_q, int n_k, float scale_log2, const int8_t* qk_src,
+                        float* lse, cudaStream_t stream);
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace rtti

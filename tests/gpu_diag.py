@@ -222,6 +222,20 @@ CASES = {
 }
 
 
+# Not collected by pytest (tests/test_kernels_gpu.py parametrizes over CASES only): schedules that have been written but
+# not yet verified on hardware. Run by hand:  python tests/gpu_diag.py v4:self_1024
+EXPERIMENTAL = {
+    "v4:self_1tile": lambda: attn_case(1, 1, 64, 128, 128),
+    "v4:self_small": lambda: attn_case(2, 2, 64, 256, 256),
+    "v4:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    "v4:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
+    "v4:odd_tiles": lambda: attn_case(2, 2, 64, 320, 320, want_lse=True),
+    "v4:self_inject": lambda: attn_case(4, 2, 64, 256, 256, qk_src=[0, 1, 1, 1]),
+    "v4:d40": lambda: attn_case(2, 8, 40, 256, 256),
+    "v4:self_4096": lambda: attn_case(1, 10, 64, 4096, 4096, fused_qkv=True),
+}
+
+
 def case_env(name):
     """Environment of the subprocess that runs case `name` (the prefix selects an attention schedule switch)."""
     env = dict(os.environ)
@@ -239,11 +253,14 @@ def case_env(name):
         env["RTTI_ATTN_ILP"] = "1"
     if name.startswith("pf:"):
         env["RTTI_ATTN_PF"] = "1"
+    if name.startswith("v4:"):
+        env["RTTI_ATTN_V4"] = "1"
     return env
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
-        ok = CASES[sys.argv[1]]()
+        os.environ.update(case_env(sys.argv[1]))   # the library reads its switches at load time (first op call)
+        ok = {**CASES, **EXPERIMENTAL}[sys.argv[1]]()
         sys.exit(0 if ok else 1)
     summary = []
     for name in CASES:
