@@ -15,6 +15,14 @@
 //     registers that quarter q-1 of S_j just vacated, lands while quarter q of S_j is exponentiated, and its partial row
 //     max is taken in the same basic block as the next quarter's exponentials. Live registers: 64 + 16 + packed P.
 // Everything else (TMA producer, in-place fp16 P, TS-operand PV MMA, lazy rescale, epilogue) is v3's.
+//
+// Known issue to look at first (cuobjdump -sass, order of LDTM vs MUFU.EX2 in the two unrolled tile bodies): ptxas is free
+// to re-order the PTX stream and, in the sB->sA copy of the tile body, currently sinks all four quarter loads behind the
+// 64 exponentials (in the sA->sB copy only the last one), which removes the overlap this kernel exists for; `asm volatile`
+// on the exponentials does not help because it only orders the statements for the front end, not for ptxas. Candidates:
+// a true register dependency between a quarter's load and the following quarter's exponentials, or a non-unrolled
+// quarter loop over shared-memory-free register tiles (dynamic register indexing is not available, so the body must be
+// written out per quarter with an opaque, always-taken branch between quarters).
 #include <cstdlib>
 #include <type_traits>
 
@@ -44,6 +52,14 @@ constexpr int OFF_BAR = OFF_O + Q_TILE;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // ~98 KB -> 2 CTAs / SM
 constexpr uint32_t O_COL = 64 * NSBUF;             // 192
 constexpr int THREADS = 192;
+
+// volatile: keeps the exponentials in program order relative to the (volatile) tcgen05.ld / wait::ld statements — the
+// scheduler otherwise hoists all 64 MUFU ops of a tile above the quarter loads and the pipelining is gone (seen in SASS).
+__device__ __forceinline__ float ex2_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
 }  // namespace v4
 
 __global__ void __launch_bounds__(v4::THREADS, 2)
@@ -162,8 +178,8 @@ attn_self_v4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     auto exp_q = [&](int q, const float (&s)[64], uint32_t (&pk)[32], float (&rs)[2]) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float e0 = ex2_approx(fmaf(s[16 * q + 2 * i], p.scale_log2, -m_ref));
-        const float e1 = ex2_approx(fmaf(s[16 * q + 2 * i + 1], p.scale_log2, -m_ref));
+        const float e0 = ex2_ordered(fmaf(s[16 * q + 2 * i], p.scale_log2, -m_ref));
+        const float e1 = ex2_ordered(fmaf(s[16 * q + 2 * i + 1], p.scale_log2, -m_ref));
         rs[i & 1] += e0 + e1;
         pk[8 * q + i] = pack_half2(e0, e1);
       }
