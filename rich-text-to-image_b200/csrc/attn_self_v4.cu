@@ -16,13 +16,11 @@
 //     max is taken in the same basic block as the next quarter's exponentials. Live registers: 64 + 16 + packed P.
 // Everything else (TMA producer, in-place fp16 P, TS-operand PV MMA, lazy rescale, epilogue) is v3's.
 //
-// Known issue to look at first (cuobjdump -sass, order of LDTM vs MUFU.EX2 in the two unrolled tile bodies): ptxas is free
-// to re-order the PTX stream and, in the sB->sA copy of the tile body, currently sinks all four quarter loads behind the
-// 64 exponentials (in the sA->sB copy only the last one), which removes the overlap this kernel exists for; `asm volatile`
-// on the exponentials does not help because it only orders the statements for the front end, not for ptxas. Candidates:
-// a true register dependency between a quarter's load and the following quarter's exponentials, or a non-unrolled
-// quarter loop over shared-memory-free register tiles (dynamic register indexing is not available, so the body must be
-// written out per quarter with an opaque, always-taken branch between quarters).
+// Scheduling note (checked with cuobjdump -sass: order of LDTM vs MUFU.EX2): ptxas is free to re-order the PTX stream and,
+// with a straight-line tile body, sinks the quarter loads behind the 64 exponentials (`asm volatile` only orders the
+// statements for the front end). Each quarter's exponentials therefore sit in their own basic block behind an
+// always-true-but-opaque branch; the SASS of both unrolled tile bodies is then LDTM, 16 MUFU, LDTM, 16 MUFU, ... as
+// intended. Cost to look at on hardware: 168 registers with 72 bytes of spill stores per thread.
 #include <cstdlib>
 #include <type_traits>
 
@@ -160,6 +158,9 @@ attn_self_v4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const bool row_ok = (q0 + row) < p.n_q;
     float m_ref = -INFINITY, l = 0.f;
     float sA[64], sB[64];
+    // always true, but not provably so: every quarter's exponentials become their own basic block, which keeps ptxas from
+    // sinking the tcgen05.ld of the next quarter behind them (see the header)
+    const bool opaque = p.batch != -0x5eed;
 
     auto mask_q = [&](int j, int q, float (&s)[64]) {   // keys beyond n_k in the last tile
       const int valid = p.n_k - j * KT;
@@ -221,30 +222,31 @@ attn_self_v4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tc_fence_after();
         tmem_ld16(tlane + n_col, reinterpret_cast<uint32_t*>(nxt));
       }
-      exp_q(0, cur, pk, rs);
+      if (opaque) exp_q(0, cur, pk, rs);
       if constexpr (has_next) {
         tmem_wait_ld_regs16(reinterpret_cast<uint32_t*>(nxt));
         mask_q(j + 1, 0, nxt);
         tmem_ld16(tlane + n_col + 16, reinterpret_cast<uint32_t*>(nxt) + 16);
         mq0 = max_q(0, nxt);
       }
-      exp_q(1, cur, pk, rs);
+      if (opaque) exp_q(1, cur, pk, rs);
       if constexpr (has_next) {
         tmem_wait_ld_regs16(reinterpret_cast<uint32_t*>(nxt) + 16);
         mask_q(j + 1, 1, nxt);
         tmem_ld16(tlane + n_col + 32, reinterpret_cast<uint32_t*>(nxt) + 32);
         mq1 = max_q(1, nxt);
       }
-      exp_q(2, cur, pk, rs);
+      tmem_st16(tlane + s_col, pk);          // first half of packed P_j (S_j is entirely in registers by now)
+      if (opaque) exp_q(2, cur, pk, rs);
       if constexpr (has_next) {
         tmem_wait_ld_regs16(reinterpret_cast<uint32_t*>(nxt) + 32);
         mask_q(j + 1, 2, nxt);
         tmem_ld16(tlane + n_col + 48, reinterpret_cast<uint32_t*>(nxt) + 48);
         mq2 = max_q(2, nxt);
       }
-      exp_q(3, cur, pk, rs);
+      if (opaque) exp_q(3, cur, pk, rs);
       l += rs[0] + rs[1];
-      tmem_st32(tlane + s_col, pk);          // packed P_j over the first 32 columns of its own S buffer
+      tmem_st16(tlane + s_col + 16, pk + 16);   // second half: P_j occupies the first 32 columns of its own S buffer
       if constexpr (has_next) {
         tmem_wait_ld_regs16(reinterpret_cast<uint32_t*>(nxt) + 48);
         mask_q(j + 1, 3, nxt);
