@@ -311,7 +311,10 @@ __device__ __forceinline__ float exp2_poly(float x) {
 // PF: software-pipelined softmax — the TMEM load of S_{j+1} is issued before the exponentials of tile j and lands
 // half-way through them, and its row max is computed in the same basic block as the second half of the exponentials,
 // so the load latency and the max chain of the next tile hide under the MUFU work of the current one.
-template <int POLY, bool ILP, bool PF>
+// X2: scale/shift and row sums with the packed fp32 instructions of sm_100 (fma.rn.f32x2 / add.rn.f32x2 -> FFMA2 / FADD2):
+// 64 fewer issue slots per tile in a warp whose every instruction costs about its issue time. Same products and
+// roundings per element; only the order of the row-sum additions differs.
+template <int POLY, bool ILP, bool PF, bool X2 = false>
 __global__ void __launch_bounds__(v3::THREADS, 2)
 attn_self_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
@@ -544,18 +547,31 @@ attn_self_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             }
           }
         }
-        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[32];
-  #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x0 = fmaf(s[2 * i], p.scale_log2, -m_ref);
-          const float x1 = fmaf(s[2 * i + 1], p.scale_log2, -m_ref);
-          const float e0 = (POLY > 0 && (2 * i) % POLY == POLY - 1) ? exp2_poly(x0) : ex2_approx(x0);
-          const float e1 = (POLY > 0 && (2 * i + 1) % POLY == POLY - 1) ? exp2_poly(x1) : ex2_approx(x1);
-          rs4[ILP ? (i & 3) : 0] += e0 + e1;
-          pk[i] = pack_half2(e0, e1);
+        if constexpr (X2) {
+          const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+          float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float2 x = fma_f32x2(make_float2(s[2 * i], s[2 * i + 1]), sc2, nm2);
+            const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            acc[i & 1] = add_f32x2(acc[i & 1], e);
+            pk[i] = pack_half2(e.x, e.y);
+          }
+          l += (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y);
+        } else {
+          float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x0 = fmaf(s[2 * i], p.scale_log2, -m_ref);
+            const float x1 = fmaf(s[2 * i + 1], p.scale_log2, -m_ref);
+            const float e0 = (POLY > 0 && (2 * i) % POLY == POLY - 1) ? exp2_poly(x0) : ex2_approx(x0);
+            const float e1 = (POLY > 0 && (2 * i + 1) % POLY == POLY - 1) ? exp2_poly(x1) : ex2_approx(x1);
+            rs4[ILP ? (i & 3) : 0] += e0 + e1;
+            pk[i] = pack_half2(e0, e1);
+          }
+          l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
         }
-        l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
         tmem_st32(tlane + s_col, pk);          // packed P_j over the first 32 columns of its own S buffer
         tmem_wait_st();
         tc_fence_before();
@@ -606,11 +622,13 @@ int launch_attn_self_v3(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
   static const bool ilp = [] { const char* e = getenv("RTTI_ATTN_ILP"); return e ? atoi(e) != 0 : V3_ILP_DEFAULT; }();
   using KernelT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnV2Params);
   static const bool pf = [] { const char* e = getenv("RTTI_ATTN_PF"); return e ? atoi(e) != 0 : V3_PF_DEFAULT; }();
+  static const bool x2 = [] { const char* e = getenv("RTTI_ATTN_X2"); return e ? atoi(e) != 0 : false; }();   // unverified on hardware
   static const KernelT kernel = [] {
     KernelT k = ilp ? attn_self_v3_kernel<0, true, false> : attn_self_v3_kernel<0, false, false>;
     if (poly == 4) k = ilp ? attn_self_v3_kernel<4, true, false> : attn_self_v3_kernel<4, false, false>;
     if (poly == 8) k = ilp ? attn_self_v3_kernel<8, true, false> : attn_self_v3_kernel<8, false, false>;
     if (pf) k = attn_self_v3_kernel<0, true, true>;
+    if (x2) k = attn_self_v3_kernel<0, false, false, true>;
     return k;
   }();
   static const bool configured =

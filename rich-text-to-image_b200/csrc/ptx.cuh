@@ -241,6 +241,22 @@ __device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
   asm("ex2.approx.f16x2 %0, %1;\n" : "=r"(y) : "r"(x));
   return y;
 }
+// packed fp32 pairs (sm_100: FFMA2 / FADD2), one issue slot for two lanes of work
+__device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)),
+        "l"(*reinterpret_cast<const uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;\n"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -233,6 +233,10 @@ EXPERIMENTAL = {
     "v4:self_inject": lambda: attn_case(4, 2, 64, 256, 256, qk_src=[0, 1, 1, 1]),
     "v4:d40": lambda: attn_case(2, 8, 40, 256, 256),
     "v4:self_4096": lambda: attn_case(1, 10, 64, 4096, 4096, fused_qkv=True),
+    # v3 with packed fp32 scale/shift and row sums (FFMA2 / FADD2): RTTI_ATTN_X2=1
+    "x2:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
+    "x2:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
+    "x2:d40": lambda: attn_case(2, 8, 40, 256, 256),
 }
 
 
@@ -255,6 +259,8 @@ def case_env(name):
         env["RTTI_ATTN_PF"] = "1"
     if name.startswith("v4:"):
         env["RTTI_ATTN_V4"] = "1"
+    if name.startswith("x2:"):
+        env["RTTI_ATTN_X2"] = "1"
     return env
 
 if __name__ == "__main__":
