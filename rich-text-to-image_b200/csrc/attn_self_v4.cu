@@ -176,13 +176,15 @@ attn_self_v4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int i = 2; i < 16; i += 2) { a = fmaxf(a, s[16 * q + i]); c = fmaxf(c, s[16 * q + i + 1]); }
       return fmaxf(a, c);
     };
-    auto exp_q = [&](int q, const float (&s)[64], uint32_t (&pk)[32], float (&rs)[2]) {
+    // packed fp32 scale/shift and row sums (FFMA2 / FADD2): half the issue slots of the scalar form
+    auto exp_q = [&](int q, const float (&s)[64], uint32_t (&pk)[32], float2 (&rs)[2]) {
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float e0 = ex2_ordered(fmaf(s[16 * q + 2 * i], p.scale_log2, -m_ref));
-        const float e1 = ex2_ordered(fmaf(s[16 * q + 2 * i + 1], p.scale_log2, -m_ref));
-        rs[i & 1] += e0 + e1;
-        pk[8 * q + i] = pack_half2(e0, e1);
+        const float2 x = fma_f32x2(make_float2(s[16 * q + 2 * i], s[16 * q + 2 * i + 1]), sc2, nm2);
+        const float2 e = make_float2(ex2_ordered(x.x), ex2_ordered(x.y));
+        rs[i & 1] = add_f32x2(rs[i & 1], e);
+        pk[8 * q + i] = pack_half2(e.x, e.y);
       }
     };
     // one tile: exponentiate S_j held in `cur` (row max mx), meanwhile bring S_{j+1} into `nxt` quarter by quarter
@@ -215,7 +217,7 @@ attn_self_v4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       const uint32_t n_col = 64u * ((j + 1) % NSBUF);
       uint32_t pk[32];
-      float rs[2] = {0.f, 0.f};
+      float2 rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       float mq0 = -INFINITY, mq1 = -INFINITY, mq2 = -INFINITY, mq3 = -INFINITY;
       if constexpr (has_next) {
         mbar_wait(&s_full[(j + 1) % NSBUF], ((j + 1) / NSBUF) & 1);   // issued two tiles ago: normally no wait
@@ -245,7 +247,7 @@ attn_self_v4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mq2 = max_q(2, nxt);
       }
       if (opaque) exp_q(3, cur, pk, rs);
-      l += rs[0] + rs[1];
+      l += (rs[0].x + rs[0].y) + (rs[1].x + rs[1].y);
       tmem_st16(tlane + s_col + 16, pk + 16);   // second half: P_j occupies the first 32 columns of its own S buffer
       if constexpr (has_next) {
         tmem_wait_ld_regs16(reinterpret_cast<uint32_t*>(nxt) + 48);
