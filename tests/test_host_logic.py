@@ -136,3 +136,36 @@ def test_richtext_parse_and_region_inputs():
     tfd, cids = ru.get_gradient_guidance_input(M(), base_tokens, cspans, crgbs, tfd, color_guidance_weight=0.5)
     assert [i.tolist() for i in cids] == [[3], [1, 2, 4, 5, 6, 7]] and tfd["color_guidance_weight"] == 0.5
     assert ru.find_nearest_color([250, 10, 5]) == "red"
+
+
+def test_c_abi_rejects_bad_arguments_without_launching():
+    """Error behaviour of the boundary (include/rtti_b200.h): bad pointers / shapes / alignment return the documented
+    negative code before any CUDA call — checked through raw ctypes, which is what a foreign-language binding would do."""
+    import ctypes
+    from rtti_b200 import _lib
+    lib = _lib.load()
+    V = ctypes.c_void_p
+    buf = (ctypes.c_char * 4096)()
+    a = (ctypes.addressof(buf) + 15) // 16 * 16
+    ARG, SHAPE, ALIGN = -1, -2, -3
+    # rtti_halo_exchange(pad_local, pad_up, pad_down, rows, row_elems, flags_local, flags_up, flags_down, seq, stream)
+    assert lib.rtti_halo_exchange(V(0), V(0), V(0), 4, 64, V(a), V(0), V(0), 1, V(0)) == ARG
+    assert lib.rtti_halo_exchange(V(a), V(0), V(0), 4, 6, V(a), V(0), V(0), 1, V(0)) == SHAPE
+    assert lib.rtti_halo_exchange(V(a + 4), V(0), V(0), 4, 64, V(a), V(0), V(0), 1, V(0)) == ALIGN
+    assert lib.rtti_halo_exchange(V(a), V(a), V(0), 4, 64, V(a), V(0), V(0), 1, V(0)) == ARG      # neighbour without flags
+    peers = (V * 2)(V(a), V(a))
+    gn = lambda hw_local, hw_total, c, groups, world, rank: lib.rtti_gn32_silu_fwd_striped(
+        V(a), V(0), V(a), V(a), V(a), V(a), V(a), hw_local, hw_total, c, groups, 1e-6, 1, peers, peers, world, rank, 1, V(0))
+    assert gn(16, 32, 256, 64, 2, 0) == SHAPE      # more than 32 groups
+    assert gn(16, 32, 64, 32, 2, 2) == ARG         # rank outside the world
+    assert gn(16, 8, 64, 32, 2, 0) == ARG          # stripe larger than the tensor
+    assert gn(16, 32, 66, 33, 2, 0) == SHAPE       # channels not a multiple of 4
+    assert lib.rtti_add_bias_f32(V(a), V(a), V(0), V(a), 4, 6, V(0)) == SHAPE
+    assert lib.rtti_add_bias_f32(V(0), V(a), V(0), V(a), 4, 8, V(0)) == ARG
+    # rtti_gather_blend_step(peer_slots, peer_flags, world, rank, slot_owner, n_slots, n_regions, masks, n, ...)
+    owner = (ctypes.c_int * 4)(0, 0, 1, 1)
+    gb = lambda world, rank, n: lib.rtti_gather_blend_step(peers, peers, world, rank, owner, 4, 3, V(a), n, 7.5, V(a), V(0), V(0),
+                                                            V(0), V(0), -0.1, 1, V(0))
+    assert gb(17, 0, 64) == ARG                    # more ranks than the kernel's table
+    assert gb(2, 0, 60) == SHAPE                   # n not a multiple of 8
+    assert lib.rtti_version() >= 100
