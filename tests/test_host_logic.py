@@ -169,3 +169,20 @@ def test_c_abi_rejects_bad_arguments_without_launching():
     assert gb(17, 0, 64) == ARG                    # more ranks than the kernel's table
     assert gb(2, 0, 60) == SHAPE                   # n not a multiple of 8
     assert lib.rtti_version() >= 100
+
+
+def test_pass_batch_matches_the_reference_call_sequence():
+    """models/region_diffusion_sdxl.py:787-821 runs 2 + 2*inject + (N-1) UNet calls per step: uncond and base prompt on
+    the latents, (uncond, base) on the reference latents when injecting, one call per region prompt."""
+    from rtti_b200.region_diffusion_sdxl import RegionDiffusionXL
+    for n_regions in (1, 3, 5, 8, 10):
+        for inject in (False, True):
+            passes = RegionDiffusionXL.build_pass_batch(None, n_regions, inject)
+            assert len(passes) == 2 + 2 * inject + (n_regions - 1)
+            kinds = "".join(p["kind"] for p in passes)
+            assert kinds == "AB" + ("CD" if inject else "") + "E" * (n_regions - 1)
+            assert [p["ctx"] for p in passes if p["kind"] in "AC"] == [0] * (1 + inject)          # unconditional row
+            assert all(p["ctx"] == n_regions for p in passes if p["kind"] in "BD")                # base prompt = last row
+            assert [p["ctx"] for p in passes if p["kind"] == "E"] == list(range(1, n_regions))    # region prompts in order
+            assert [p["ref"] for p in passes] == [p["kind"] in "CD" for p in passes]              # reference-latent passes
+    assert len(RegionDiffusionXL.build_pass_batch(None, 5, True)) == 8        # bench.py's workload
