@@ -202,6 +202,9 @@ def color_loss_fwd_bwd(decoded, masks, target_rgb):
         _req(t, torch.float32, nme); assert t.is_contiguous()
     R = masks.shape[0]
     hw = decoded.numel() // 3
+    if decoded.shape[0] != 3 or masks[0].numel() != hw or tuple(target_rgb.shape) != (R, 3):
+        raise _lib.RttiError(f"color_loss_fwd_bwd: decoded {tuple(decoded.shape)}, masks {tuple(masks.shape)}, "
+                             f"target_rgb {tuple(target_rgb.shape)} do not agree (need [3,H,W], [R,H,W], [R,3])")
     n = lib.rtti_color_loss_workspace_elems(R, hw)
     ws = _cl_ws.get(decoded.device.index)
     if ws is None or ws.numel() < n:
@@ -219,6 +222,8 @@ def color_loss_fwd_bwd(decoded, masks, target_rgb):
 def latent_guidance_update(latents, grad, atten_all, weight):
     lib = _lib.load()
     _req(latents, _F16, "latents"); _req(grad, torch.float32, "grad"); _req(atten_all, torch.float32, "atten_all")
+    if grad.numel() != latents.numel() or atten_all.numel() != latents.numel():
+        raise _lib.RttiError("latent_guidance_update: latents, grad and atten_all must have the same number of elements")
     out = torch.empty_like(latents)
     rc = lib.rtti_latent_guidance_update(_ptr(latents), _ptr(grad.contiguous()), _ptr(atten_all.contiguous()),
                                          float(weight), _ptr(out), latents.numel(), _stream())
@@ -230,6 +235,8 @@ def latent_guidance_update(latents, grad, atten_all, weight):
 def bg_inject_blend(latents, latents_ref, mask):
     lib = _lib.load()
     _req(latents, _F16, "latents"); _req(latents_ref, _F16, "latents_ref"); _req(mask, torch.float32, "mask")
+    if latents_ref.numel() != latents.numel() or mask.numel() != latents.numel():
+        raise _lib.RttiError("bg_inject_blend: latents, latents_ref and mask must have the same number of elements")
     out = torch.empty_like(latents)
     rc = lib.rtti_bg_inject_blend(_ptr(latents), _ptr(latents_ref), _ptr(mask.contiguous()), _ptr(out),
                                   latents.numel(), _stream())

@@ -120,8 +120,11 @@ class RegionDiffusionXL:
         rtti_color_loss_fwd_bwd and the VAE (third-party) in PyTorch autograd with frozen weights."""
         x0, alpha = self.predict_x0(latents, noise_pred, t)
         sf = self.vae.config.scaling_factor
-        masks = torch.stack([m[0, 0].to(self.device, torch.float32) for m in tfd["color_obj_atten"]]).contiguous()
-        tgt = torch.stack([r.reshape(3).to(self.device, torch.float32) for r in tfd["target_RGB"]]).contiguous()
+        # the reference pairs maps and targets with zip() (sdxl.py:857 / region_diffusion.py:159): sample.py hands over
+        # R colour maps + the background map but only R target colours, and the background map is dropped
+        n_col = min(len(tfd["color_obj_atten"]), len(tfd["target_RGB"]))
+        masks = torch.stack([m[0, 0].to(self.device, torch.float32) for m in tfd["color_obj_atten"][:n_col]]).contiguous()
+        tgt = torch.stack([r.reshape(3).to(self.device, torch.float32) for r in tfd["target_RGB"][:n_col]]).contiguous()
 
         def grad_image(img):
             loss, g = ops.color_loss_fwd_bwd(img[0].contiguous(), masks, tgt)
