@@ -8,7 +8,8 @@
 //     font-size token re-weighting (attention_processor.py:387-399) and the optional capture of
 //     the head-averaged probability map P-bar (attention_processor.py:1181 + the token-map hook
 //     models/region_diffusion_sdxl.py:965-992) fused in-kernel;
-//   * self-attention (HW keys, KT=128 tiles, online softmax) with the self-attention *injection*
+//   * self-attention with head_dim > 64 (SD1.5: 80, 160; KT=128 tiles, online softmax; head_dim <= 64 goes to
+//     attn_self.cu) with the self-attention *injection*
 //     of the region passes (models/region_diffusion_sdxl.py:1018-1029: real_attn_probs replaces
 //     softmax(QK^T)) expressed as a per-batch-entry Q/K source index `qk_src`: entry b attends with
 //     the scores of entry qk_src[b] and its own V, which is what P_ref @ V_b computes.
@@ -45,7 +46,7 @@ struct AttnParams {
   float* lse;   // [batch, heads, n_q] fp32, log2-domain log-sum-exp of the scaled scores (optional)
 };
 
-template <int KT, int NDCH, bool CAPTURE, bool EXP16 = false>
+template <int KT, int NDCH, bool CAPTURE>
 struct AttnCfg {
   static constexpr int NQBUF = (KT == 80 && NDCH < 3) ? 2 : 1;
   static constexpr int NSTAGE = (KT == 128 && NDCH == 3) ? 1 : 2;
@@ -54,27 +55,22 @@ struct AttnCfg {
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NQBUF * NDCH * Q_TILE;
   static constexpr int OFF_V = OFF_K + NSTAGE * NDCH * KV_TILE;
-  // KT == 64 (3 CTAs/SM): the output staging tile aliases the Q tile (one head per CTA, Q is dead by then)
-  static constexpr int OFF_O = (KT == 64) ? OFF_Q : OFF_V + NSTAGE * NDCH * KV_TILE;
-  static constexpr int OFF_BAR = (KT == 64) ? OFF_V + NSTAGE * NDCH * KV_TILE : OFF_O + NDCH * Q_TILE;
+  static constexpr int OFF_O = OFF_V + NSTAGE * NDCH * KV_TILE;
+  static constexpr int OFF_BAR = OFF_O + NDCH * Q_TILE;
   static constexpr int OFF_FS = OFF_BAR + 256;
-  // EXP16: a 2 KB all-ones fp16 tile = B operand of the row-sum MMA (L += P * 1), 1024-aligned
-  static constexpr int OFF_ONES = ((OFF_FS + 128 * 4 + 1023) / 1024) * 1024;
-  static constexpr int SMEM_BYTES = (EXP16 ? OFF_ONES + 2048 : OFF_FS + 128 * 4) + 1024 /*alignment slack*/;
-  static constexpr uint32_t O_COL = (KT == 64) ? 64 : 128;
-  static constexpr uint32_t L_COL = O_COL + 64 * NDCH;  // EXP16: 16 columns holding the running row sum
-  static constexpr uint32_t TMEM_COLS = (KT == 64) ? 128 : ((128 + 64 * NDCH) <= 256 ? 256 : 512);
-  static constexpr int MIN_CTAS = (KT == 64) ? 3 : ((NDCH == 1 && !CAPTURE) ? 2 : 1);
-  static constexpr int MAX_REGS = MIN_CTAS == 3 ? 112 : (MIN_CTAS == 2 ? 168 : 255);
+  static constexpr int SMEM_BYTES = OFF_FS + 128 * 4 + 1024 /*alignment slack*/;
+  static constexpr uint32_t O_COL = 128;
+  static constexpr uint32_t TMEM_COLS = (128 + 64 * NDCH) <= 256 ? 256 : 512;
+  static constexpr int MIN_CTAS = (NDCH == 1 && !CAPTURE) ? 2 : 1;
+  static constexpr int MAX_REGS = MIN_CTAS == 2 ? 168 : 255;
 };
 
-template <int KT, int NDCH, bool CAPTURE, bool EXP16 = false>
-__global__ void __launch_bounds__(192) __maxnreg__((AttnCfg<KT, NDCH, CAPTURE, EXP16>::MAX_REGS))
+template <int KT, int NDCH, bool CAPTURE>
+__global__ void __launch_bounds__(192) __maxnreg__((AttnCfg<KT, NDCH, CAPTURE>::MAX_REGS))
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                 const AttnParams p) {
-  using C = AttnCfg<KT, NDCH, CAPTURE, EXP16>;
-  static_assert(!EXP16 || (KT == 128 && NDCH == 1), "EXP16 path: 128-key tiles, head_dim <= 64");
+  using C = AttnCfg<KT, NDCH, CAPTURE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -109,11 +105,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // dense signed weight per key; duplicates in word_pos: last write wins, as the reference's
     // advanced-index assignment does on CPU (attention_processor.py:393-396)
     if (threadIdx.x < KT) fs_w[threadIdx.x] = 1.f;
-  }
-  if (EXP16) {
-    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + C::OFF_ONES);
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) ones[i] = 0x3C003C00u;  // fp16 1.0 pairs
-    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -186,11 +177,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               const uint64_t db = umma_desc_sw128(smem_base + C::OFF_V + (st * NDCH + c) * C::KV_TILE + kk * 2048,
                                                   C::KV_TILE, 1024);
               mma_f16_ts(tmem + C::O_COL + 64 * c, tmem + kk * 8, db, IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
-            }
-            if (EXP16) {  // L[128 x 16] += P[128 x 16 keys] * ones: the softmax denominator on the tensor pipe
-              constexpr uint32_t IDESC_L = umma_idesc_f16(128, 16, 0, 1);
-              const uint64_t dl = umma_desc_sw128(smem_base + C::OFF_ONES, 2048, 1024);
-              mma_f16_ts(tmem + C::L_COL, tmem + kk * 8, dl, IDESC_L, (j > 0 || kk > 0) ? 1u : 0u);
             }
           }
           tc_commit(&kv_empty[st]);
@@ -271,60 +257,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_before();
         mbar_arrive(p_full);
         ++tit;
-      } else if constexpr (KT == 64) {
-        // ---- key tiles of 64, three CTAs per SM: the 64-column row of S lives in registers (one TMEM round trip)
-        for (int j = 0; j < p.n_k_tiles; ++j, ++tit) {
-          mbar_wait(s_full, tit & 1);
-          tc_fence_after();
-          const int valid = p.n_k - j * KT;
-          float s[64];
-          tmem_ld32(tlane, reinterpret_cast<uint32_t*>(s));
-          tmem_ld32(tlane + 32, reinterpret_cast<uint32_t*>(s) + 32);
-          tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s));
-          tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s) + 32);
-          if (valid < KT) {
-#pragma unroll
-            for (int i = 0; i < KT; ++i)
-              if (i >= valid) s[i] = -INFINITY;
-          }
-          float mx = s[0];
-#pragma unroll
-          for (int i = 1; i < KT; ++i) mx = fmaxf(mx, s[i]);
-          const float mxs = mx * p.scale_log2;
-          if (j == 0) {
-            m_ref = mxs;
-          } else {
-            const bool need = mxs > m_ref + 8.f;
-            if (__any_sync(0xffffffffu, need)) {
-              const float alpha = need ? ex2_approx(m_ref - mxs) : 1.f;
-              if (need) m_ref = mxs;
-              l *= alpha;
-#pragma unroll
-              for (int c = 0; c < 4 * NDCH; ++c) {  // 16 columns at a time: the S row stays live in registers
-                uint32_t o[16];
-                tmem_ld16(tlane + C::O_COL + 16 * c, o);
-                tmem_wait_ld_regs16(o);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                tmem_st16(tlane + C::O_COL + 16 * c, o);
-              }
-            }
-          }
-          float rowsum = 0.f;
-          uint32_t pk[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e0 = ex2_approx(fmaf(s[2 * i], p.scale_log2, -m_ref));
-            const float e1 = ex2_approx(fmaf(s[2 * i + 1], p.scale_log2, -m_ref));
-            rowsum += e0 + e1;
-            pk[i] = pack_half2(e0, e1);
-          }
-          l += rowsum;
-          tmem_st32(tlane, pk);
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive(p_full);
-        }
       } else {
         // ---- key tiles of 128 with online softmax; S is streamed from TMEM twice (max, then exp)
         //      in 32-column chunks so the row never has to live in registers.
@@ -369,39 +301,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                 tmem_st32(tlane + C::O_COL + 32 * c, o);
               }
-              if (EXP16) {
-                uint32_t o[16];
-                tmem_ld16(tlane + C::L_COL, o);
-                tmem_wait_ld_regs16(o);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                tmem_st16(tlane + C::L_COL, o);
-              }
             }
           }
           float rowsum = 0.f;
-          if constexpr (EXP16) {
-            // packed-fp16 exponentials (2 per MUFU op); the row sum is accumulated by the L MMA, not here
-            uint32_t buf[2][32];
-            tmem_ld32(tlane, buf[0]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              tmem_wait_ld_regs32(buf[c & 1]);
-              if (c + 1 < 4) tmem_ld32(tlane + 32 * (c + 1), buf[(c + 1) & 1]);
-              uint32_t pk[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float x0 = fmaf(__uint_as_float(buf[c & 1][2 * i]), p.scale_log2, -m_ref);
-                float x1 = fmaf(__uint_as_float(buf[c & 1][2 * i + 1]), p.scale_log2, -m_ref);
-                if (valid < 32 * (c + 1)) {
-                  if (32 * c + 2 * i >= valid) x0 = -INFINITY;
-                  if (32 * c + 2 * i + 1 >= valid) x1 = -INFINITY;
-                }
-                pk[i] = ex2_f16x2(pack_half2(x0, x1));
-              }
-              tmem_st16(tlane + 16 * c, pk);
-            }
-          } else {
+          {
             uint32_t buf[2][32];
             tmem_ld32(tlane, buf[0]);
 #pragma unroll
@@ -441,12 +344,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // ---- epilogue for this head
       mbar_wait(o_full, hit & 1);
       tc_fence_after();
-      if (EXP16) {
-        uint32_t lv[16];
-        tmem_ld16(tlane + C::L_COL, lv);
-        tmem_wait_ld_regs16(lv);
-        l = __uint_as_float(lv[0]);
-      }
       const float inv_l = (KT == 80) ? 1.f : 1.f / l;
       if (threadIdx.x == 0) tma_store_wait_read();  // previous head's store has drained the staging tile
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
@@ -497,11 +394,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int KT, int NDCH, bool CAPTURE, bool EXP16 = false>
+template <int KT, int NDCH, bool CAPTURE>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                   const AttnParams& p, dim3 grid, cudaStream_t stream) {
-  using C = AttnCfg<KT, NDCH, CAPTURE, EXP16>;
-  auto kern = attn_fwd_kernel<KT, NDCH, CAPTURE, EXP16>;
+  using C = AttnCfg<KT, NDCH, CAPTURE>;
+  auto kern = attn_fwd_kernel<KT, NDCH, CAPTURE>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
@@ -516,18 +413,9 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 
 using namespace rtti;
 
-// A/B switch for profiling: RTTI_ATTN_KT64=1 selects the 64-key-tile / 3-CTA-per-SM kernel for head_dim <= 64.
-// RTTI_ATTN_EXP16=1 selects packed-fp16 exponentials + tensor-core row sums in the head_dim<=64 self-attention
-// kernel. Measured 21 % SLOWER than fp32 exponentials on B200 (profiles/r01_kernels_v3_*.jsonl): sm_100 executes
-// ex2.approx.f16x2 as two MUFU.EX2.F16 ops (the doubled SFU rate is an sm_103 feature), so it is off by default.
-static const bool g_exp16 = [] { const char* e = getenv("RTTI_ATTN_EXP16"); return e && e[0] == '1'; }();
-// RTTI_ATTN_V1=1 keeps the sequential 2-CTA/SM kernel of this file for head_dim <= 64 self-attention.
-static const bool g_v2 = [] { const char* e = getenv("RTTI_ATTN_V1"); return !(e && e[0] == '1'); }();
-// RTTI_ATTN_V2=1 selects the 1-CTA/SM, 2-threads-per-row schedule (v2) instead of v3 for head_dim <= 64.
-static const bool g_v3 = [] { const char* e = getenv("RTTI_ATTN_V2"); return !(e && e[0] == '1'); }();
-// RTTI_ATTN_V4=1: experimental triple-buffered / quarter-pipelined schedule (attn_self_v4.cu), same operands as v3.
-static const bool g_v4 = [] { const char* e = getenv("RTTI_ATTN_V4"); return e && e[0] == '1'; }();
-static const bool g_use_kt64 = [] { const char* e = getenv("RTTI_ATTN_KT64"); return e && e[0] == '1'; }();
+// RTTI_ATTN_MAX_GROUP = 1..6 (read once): largest number of batch entries that share one softmax in the head_dim<=64
+// self-attention kernel (attn_self.cu). Default 6; 1 disables the grouping (A/B measurements in profiles/).
+static const int g_max_group = [] { const char* e = getenv("RTTI_ATTN_MAX_GROUP"); const int v = e ? atoi(e) : 6; return v < 1 ? 1 : (v > 6 ? 6 : v); }();
 
 extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads,
                              int head_dim, int n_q, int n_k, long long q_bs, long long q_rs, long long k_bs,
@@ -548,10 +436,10 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
   if (rc != RTTI_OK) return rc;
 
   const int ndch = (head_dim + 63) / 64;
-  // 77 text keys: one 80-key tile; otherwise 128-key tiles (2 CTAs/SM). The 64-key / 3-CTA variant measured
-  // 15 % slower on B200 (profiles/r01_kernels_*.jsonl) and is kept behind RTTI_ATTN_KT64=1 for experiments.
-  const bool use_v3 = (n_k > 80 && ndch == 1 && g_v3 && !g_exp16 && !g_use_kt64 && g_v2);
-  const int KT = (n_k <= 80) ? 80 : ((ndch == 1 && (g_use_kt64 || use_v3)) ? 64 : 128);
+  // 77 text keys: one 80-key tile. Self-attention: head_dim <= 64 -> attn_self.cu (64-key tiles, grouped PV);
+  // head_dim 80 / 160 (SD1.5) -> the 128-key-tile kernel of this file.
+  const bool use_self = (n_k > 80 && ndch == 1);
+  const int KT = (n_k <= 80) ? 80 : (use_self ? 64 : 128);
   AttnParams p{};
   p.batch = batch; p.heads = heads; p.head_dim = head_dim; p.n_q = n_q; p.n_k = n_k;
   p.n_k_tiles = (n_k + KT - 1) / KT;
@@ -599,15 +487,8 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
     if (ndch == 2) RTTI_LAUNCH(80, 2, false);
     RTTI_LAUNCH(80, 3, false);
   }
-  if (use_v3) {   // 64-key tiles, MMA look-ahead, one thread per row, 2 CTAs/SM (attn_self_v2.cu)
-    if (g_v4) return launch_attn_self_v4(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.qk_src, lse, st);
-    return launch_attn_self_v3(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.qk_src, lse, st);
-  }
-  if (KT == 64) RTTI_LAUNCH(64, 1, false);
-  if (ndch == 1 && g_v2 && !g_exp16)   // software-pipelined kernel (attn_self_v2.cu): 1 CTA/SM, MMAs hidden behind exps
-    return launch_attn_self_v2(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.qk_src, lse, st);
-  if (ndch == 1 && g_exp16) return launch<128, 1, false, true>(tq, tk, tv, to, p, grid, st);
-  if (ndch == 1) RTTI_LAUNCH(128, 1, false);
+  if (use_self)
+    return launch_attn_self(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.qk_src, lse, g_max_group, st);
   if (ndch == 2) RTTI_LAUNCH(128, 2, false);
   RTTI_LAUNCH(128, 3, false);
 #undef RTTI_LAUNCH

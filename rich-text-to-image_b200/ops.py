@@ -95,7 +95,10 @@ def attention(q, k, v, heads, scale=None, qk_src=None, word_pos=None, font_size=
     _count(1)
     if prof is not None:
         ev1.record()
-        flops = 4.0 * B * heads * nq * nk * D
+        # algorithmic work = what the reference evaluates: QK^T only for entries that compute their own scores (an entry
+        # that is handed another entry's probabilities skips it, attention_processor.py:1160-1162), PV for every entry
+        own = len(set(qk_src)) if qk_src is not None else B
+        flops = 2.0 * (own + B) * heads * nq * nk * D
         nbytes = 2.0 * (2 * B * nq * C + 2 * B * nk * C)
         prof.append((ev0, ev1, "self" if nk > 80 else "cross", flops, nbytes, (B, heads, D, nq, nk)))
     return out

@@ -66,6 +66,7 @@ class RegionDiffusionXL:
         self.fused_exchange = True   # multi-GPU: fused peer-memory gather+blend kernel instead of NCCL all-gather
         self.stripe_guidance = True  # multi-GPU: colour guidance (VAE fwd+bwd) split by image rows over the ranks
         self._stripe_engines = {}
+        self.region_group = None     # torch.distributed group the passes of one image are sharded over (None = all ranks)
         self.last_step_stats = {}
 
     @classmethod
@@ -259,7 +260,7 @@ class RegionDiffusionXL:
         st.ones = torch.ones(1, latents[0].numel(), dtype=torch.float32, device=dev)
         st.passes = self.build_pass_batch(N, inject)
         st.kind = {p["kind"] + str(p.get("region", "")): k for k, p in enumerate(st.passes)}
-        st.plan = region_parallel.RegionParallelPlan(st.passes, inject)
+        st.plan = region_parallel.RegionParallelPlan(st.passes, inject, group=self.region_group)
         word_pos, font_size = tfd.get("word_pos"), tfd.get("font_size")
         if word_pos is not None and font_size is not None:
             st.word_pos = word_pos.to(dev, torch.int32).contiguous()
@@ -351,7 +352,7 @@ class RegionDiffusionXL:
             xkey = (tuple(p["kind"] for p in passes), st.latents[0].numel())
             if xkey not in self._exchanges:   # symmetric buffers are allocated once per problem shape
                 try:
-                    self._exchanges[xkey] = region_parallel.PeerExchange(passes, st.latents[0].numel(), self.device)
+                    self._exchanges[xkey] = region_parallel.PeerExchange(passes, st.latents[0].numel(), self.device, group=self.region_group)
                 except Exception as e:        # no peer-mappable memory (e.g. GPUs without P2P): NCCL all-gather path
                     import warnings
                     warnings.warn(f"rtti_b200: symmetric peer memory unavailable ({e!r}); using the NCCL all-gather exchange")

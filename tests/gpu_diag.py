@@ -103,7 +103,8 @@ def attn_case(B, H, D, nq, nk, qk_src=None, fs=False, cap=False, fused_qkv=False
     if want_lse:
         ok &= report(name + " [lse]", lse, lse_ref, 2e-3, 1e-3)
         accum = torch.full((nq, nk), 0.5, dtype=torch.float32, device="cuda")
-        ops.attn_probs_mean_accum(q[B - 1], k[B - 1], lse[B - 1], accum, H)
+        sb = qk_src[B - 1] if qk_src is not None else B - 1     # the scores of entry B-1 come from its source entry
+        ops.attn_probs_mean_accum(q[sb], k[sb], lse[B - 1], accum, H)
         torch.cuda.synchronize()
         ok &= report(name + " [probs_mean]", accum - 0.5, p_ref[B - 1].mean(0), 1e-3, 1e-2)
     return ok
@@ -191,82 +192,60 @@ CASES = {
     "d8": lambda: attn_case(2, 4, 8, 64, 77),
     "cross_xl64": lambda: attn_case(8, 10, 64, 4096, 77),
     "self_xl32": lambda: attn_case(8, 20, 64, 1024, 1024, fused_qkv=True),
-    # packed-fp16-exponential variant of the head_dim<=64 kernel (experiment, off by default): RTTI_ATTN_EXP16=1
-    "exp16:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    "exp16:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
-    # v2 schedule (1 CTA/SM, 2 threads per row): RTTI_ATTN_V2=1
-    "v2:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    "v2:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
-    # the sequential 2-CTA/SM kernel (v1) for head_dim <= 64: RTTI_ATTN_V1=1
-    "v1:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    "v1:self_inject": lambda: attn_case(4, 2, 64, 256, 256, qk_src=[0, 1, 1, 1]),
-    "v1:d40": lambda: attn_case(2, 8, 40, 256, 256),
-    # 64-key-tile / 3 CTAs per SM experiment: RTTI_ATTN_KT64=1
-    "kt64:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    # v3 with 1/4 resp. 1/2 of the exponentials evaluated by the FMA-pipe polynomial: RTTI_ATTN_POLY=4 / 2
-    "poly4:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    "poly4:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
-    "poly4:d40": lambda: attn_case(2, 8, 40, 256, 256),
-    "poly8:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    # v3 with four independent max / sum chains: RTTI_ATTN_ILP=1
-    "ilp:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    "ilp:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
-    # v3 software-pipelined softmax (S_{j+1} prefetched under the exponentials of tile j): RTTI_ATTN_PF=1
-    "pf:self_1tile": lambda: attn_case(1, 1, 64, 128, 128),
-    "pf:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    "pf:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
-    "pf:self_inject": lambda: attn_case(4, 2, 64, 256, 256, qk_src=[0, 1, 1, 1]),
-    "pf:d40": lambda: attn_case(2, 8, 40, 256, 256),
-    "pf:self_4096": lambda: attn_case(1, 10, 64, 4096, 4096, fused_qkv=True),
-    "pf:odd_tiles": lambda: attn_case(2, 2, 64, 320, 320, want_lse=True),
+    # grouped PV (attn_self.cu): entries sharing a score source are served by one softmax
+    "self_group5": lambda: attn_case(8, 2, 64, 512, 512, qk_src=[0, 1, 2, 3, 3, 3, 3, 3], fused_qkv=True),
+    "self_group3": lambda: attn_case(6, 2, 64, 320, 320, qk_src=[0, 1, 2, 3, 3, 3]),
+    "self_group2_lse": lambda: attn_case(3, 4, 64, 200, 200, qk_src=[0, 1, 1], want_lse=True),
+    "self_group7_split": lambda: attn_case(8, 2, 64, 256, 256, qk_src=[1, 1, 1, 1, 1, 1, 1, 7]),
+    "self_group_scattered": lambda: attn_case(6, 2, 64, 256, 256, qk_src=[4, 1, 4, 1, 4, 5]),
+    "self_group5_d40": lambda: attn_case(6, 8, 40, 256, 256, qk_src=[0, 1, 1, 1, 1, 1]),
+    "self_group5_xl32": lambda: attn_case(8, 20, 64, 1024, 1024, qk_src=[0, 1, 2, 3, 3, 3, 3, 3], fused_qkv=True),
+    "self_rescale": lambda: rescale_case(),
+    # grouping disabled (RTTI_ATTN_MAX_GROUP=1): every entry evaluates its own softmax from its source's Q, K
+    "g1:self_group5": lambda: attn_case(8, 2, 64, 512, 512, qk_src=[0, 1, 2, 3, 3, 3, 3, 3], fused_qkv=True),
 }
 
 
-# Not collected by pytest (tests/test_kernels_gpu.py parametrizes over CASES only): schedules that have been written but
-# not yet verified on hardware. Run by hand:  python tests/gpu_diag.py v4:self_1024
-EXPERIMENTAL = {
-    "v4:self_1tile": lambda: attn_case(1, 1, 64, 128, 128),
-    "v4:self_small": lambda: attn_case(2, 2, 64, 256, 256),
-    "v4:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    "v4:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
-    "v4:odd_tiles": lambda: attn_case(2, 2, 64, 320, 320, want_lse=True),
-    "v4:self_inject": lambda: attn_case(4, 2, 64, 256, 256, qk_src=[0, 1, 1, 1]),
-    "v4:d40": lambda: attn_case(2, 8, 40, 256, 256),
-    "v4:self_4096": lambda: attn_case(1, 10, 64, 4096, 4096, fused_qkv=True),
-    # v3 with packed fp32 scale/shift and row sums (FFMA2 / FADD2): RTTI_ATTN_X2=1
-    "x2:self_1024": lambda: attn_case(2, 4, 64, 1024, 1024, fused_qkv=True, want_lse=True),
-    "x2:self_ragged": lambda: attn_case(2, 2, 64, 200, 200, want_lse=True),
-    "x2:d40": lambda: attn_case(2, 8, 40, 256, 256),
-}
+def rescale_case():
+    """Row maxima that grow by far more than 2^8 from key tile to key tile: exercises the lazy O rescale (plain and grouped)."""
+    import torch
+    from rtti_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, H, D, T = 3, 2, 64, 384
+    q = torch.randn(B, T, H * D, device="cuda", generator=g).half()
+    k = torch.randn(B, T, H * D, device="cuda", generator=g).half()
+    v = torch.randn(B, T, H * D, device="cuda", generator=g).half()
+    ramp = torch.linspace(0.05, 3.0, T, device="cuda")[None, :, None]     # later keys score much higher
+    k = (k.float() * ramp).half()
+    ok = True
+    for src in (None, [0, 1, 1]):
+        o = ops.attention(q, k, v, H, qk_src=src, scale=1.0)
+        torch.cuda.synchronize()
+        o_ref, _, _ = ref_attention(q, k, v, H, scale=1.0, qk_src=src)
+        ok &= report(f"rescale src={src}", o, o_ref, 2e-3, 2e-2)
+    return ok
 
 
 def case_env(name):
-    """Environment of the subprocess that runs case `name` (the prefix selects an attention schedule switch)."""
+    """Environment of the subprocess that runs case `name` ("g1:" prefix = grouping disabled, every entry its own softmax)."""
     env = dict(os.environ)
-    if name.startswith("exp16:"):
-        env["RTTI_ATTN_EXP16"] = "1"; env["RTTI_ATTN_V1"] = "1"
-    if name.startswith("kt64:"):
-        env["RTTI_ATTN_KT64"] = "1"; env["RTTI_ATTN_V1"] = "1"
-    if name.startswith("v1:"):
-        env["RTTI_ATTN_V1"] = "1"
-    if name.startswith("v2:"):
-        env["RTTI_ATTN_V2"] = "1"
-    if name.startswith("poly"):
-        env["RTTI_ATTN_POLY"] = name[4:name.index(":")]
-    if name.startswith("ilp:"):
-        env["RTTI_ATTN_ILP"] = "1"
-    if name.startswith("pf:"):
-        env["RTTI_ATTN_PF"] = "1"
-    if name.startswith("v4:"):
-        env["RTTI_ATTN_V4"] = "1"
-    if name.startswith("x2:"):
-        env["RTTI_ATTN_X2"] = "1"
+    if name.startswith("g1:"):
+        env["RTTI_ATTN_MAX_GROUP"] = "1"
     return env
 
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--many":   # several cases in ONE process (bring-up; wrap in `timeout`)
+        bad = []
+        for name in sys.argv[2:]:
+            print(f"== {name}", flush=True)
+            if not CASES[name]():
+                bad.append(name)
+        print("MANY", "ALL PASS" if not bad else f"FAILED {bad}", flush=True)
+        sys.exit(1 if bad else 0)
     if len(sys.argv) > 1:
         os.environ.update(case_env(sys.argv[1]))   # the library reads its switches at load time (first op call)
-        ok = {**CASES, **EXPERIMENTAL}[sys.argv[1]]()
+        ok = CASES[sys.argv[1]]()
         sys.exit(0 if ok else 1)
     summary = []
     for name in CASES:
