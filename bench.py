@@ -263,6 +263,31 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------- product arm, SDXL configs
+def solo_check(model, fresh_state, workload, st_par, idx, dist, rank, world):
+    """--check: every rank repeats the same step sequence as a single-GPU run (all passes local, no exchange, no stripes)
+    and compares its latents with the region-parallel result: stated tolerance 0.5 % of the dynamic range + 3 %."""
+    import torch
+    solo = [dist.new_group([r]) for r in range(world)][rank]
+    saved = (model.region_group, model.fused_exchange, model.stripe_guidance)
+    model.region_group, model.stripe_guidance = solo, False
+    st = fresh_state(workload)
+    with torch.no_grad():
+        for i in idx:
+            model.rich_text_step(st, i)
+    torch.cuda.synchronize()
+    model.region_group, model.fused_exchange, model.stripe_guidance = saved
+    a, b = st_par.latents.float(), st.latents.float()
+    err = (a - b).abs()
+    tol = 5e-3 * float(b.abs().max()) + 3e-2 * b.abs()
+    res = {"max_err": float(err.max()), "mean_err": float(err.mean()), "ref_absmax": float(b.abs().max()),
+           "frac_outside_tolerance": float((err > tol).float().mean()), "steps_compared": len(idx)}
+    t = torch.tensor([res["frac_outside_tolerance"], res["max_err"]], device=a.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res["frac_outside_tolerance"], res["max_err"] = float(t[0]), float(t[1])
+    res["pass"] = res["frac_outside_tolerance"] == 0.0
+    return res
+
+
 def image_groups(world, rank, n_images):
     """Config 5: data-parallel over images first, region-parallel inside. Returns (images of this rank, ranks per image).
     world >= images: world // images ranks work on one image; else every rank owns images // world whole images."""
@@ -346,6 +371,19 @@ def run_product_xl(args, rank, world, local_rank):
     ms = float(t.item())
     for st in states:
         assert bool(torch.isfinite(st.latents.float()).all()), "non-finite latents"
+    # the blend / scheduler / guidance are replicated deterministically: all ranks of a region-parallel group must hold
+    # bit-identical latents after the timed loop (checked on every run; --check adds the single-GPU comparison)
+    ranks_identical = None
+    if world > 1:
+        h = torch.stack([st.latents.view(torch.int16).to(torch.int64).sum() for st in states]).reshape(1, -1)
+        hs = [torch.empty_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        grp = range(world) if cfg["images"] == 1 else [r for r in range(world) if image_groups(world, r, cfg["images"])[0] == my_images]
+        ranks_identical = all(bool(torch.equal(hs[r], h)) for r in grp)
+        assert ranks_identical, "latents differ between the ranks of a region-parallel group"
+    check = None
+    if args.check and world > 1 and cfg["images"] == 1:
+        check = solo_check(model, fresh_state, workloads[0], states[0], warm_idx + w_idx + t_idx, dist, rank, world)
 
     # ------------------------------------------------------------- end to end: host buffers every step
     def pin(w):
@@ -475,6 +513,7 @@ def run_product_xl(args, rank, world, local_rank):
                           "what": f"all {n_t} steps of one rich-text sampling run in schedule order through rich_text_step "
                                   "(inputs from pinned host memory once, latents read back once; CUDA graphs warm)"},
         "roofline": roof, "roofline_cross_attention": cross, "breakdown_ms": breakdown,
+        "ranks_bit_identical": ranks_identical, "single_gpu_check": check,
     }
     if world == 1 and not args.no_cpu_baseline:
         pps = passes_per_step(cfg) * cfg["images"]
@@ -623,6 +662,7 @@ def main():
     ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="rtti", choices=["rtti", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check", action="store_true", help="N > 1: also compare with a single-GPU run of the same steps")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -91,6 +91,20 @@ int rtti_add_bias_f16(const void* a, const void* b, const void* bias, void* out,
 int rtti_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int rows, int c, float eps,
                        void* stream);
 
+/* Feed-forward input projection with the GEGLU gate fused into the GEMM epilogue (tcgen05 GEMM, TMEM accumulators):
+ *   y[m, n] = (x[m, k] w[0:n, :]^T + bias[0:n]) * gelu(x w[n:2n, :]^T + bias[n:2n])     (exact erf GELU)
+ * x [m, k], w [2n, k] (the nn.Linear weight of ff.net.0.proj: value rows first, gate rows second), y [m, n], all fp16
+ * row-major contiguous; bias [2n] fp16 or NULL. Replaces models/attention.py:283-304 (GEGLU.forward: proj -> chunk ->
+ * hidden * gelu(gate)); the [m, 2n] intermediate is never written. n % 128 == 0, k % 64 == 0. */
+int rtti_ff_geglu_fwd(const void* x, const void* w, const void* bias, void* y, long long m, int n, int k, void* stream);
+
+/* h_out = fp16(a + resid + bias[c]);  y = LayerNorm(h_out) * gamma + beta, rows x c fp16, one pass over DRAM.
+ * Replaces the residual add after an attention / feed-forward projection together with the LayerNorm that follows it:
+ * models/attention.py:155-160, 172-178 (`attn(...) + hidden_states`) + :168, :181 (norm2 / norm3); the projection's
+ * bias (models/attention_processor.py:1167) is folded in. h_out may alias resid; bias may be NULL. c % 8 == 0, c <= 2048. */
+int rtti_add_bias_layernorm_fwd(const void* a, const void* resid, const void* bias, const void* gamma, const void* beta,
+                                void* h_out, void* y, int rows, int c, float eps, void* stream);
+
 /* GEGLU gate: y[rows, inner] = proj[rows, :inner] * gelu_erf(proj[rows, inner:])
  * (models/attention.py:283-304). */
 int rtti_geglu_fwd(const void* proj, void* y, int rows, int inner, void* stream);

@@ -254,6 +254,42 @@ def gen_xl_loops(ns):
     print("xl loops ok", {k: float(np.abs(v).mean()) for k, v in res.items() if v.dtype.kind == "f"})
 
 
+def gen_xl_labels(ns):
+    """Segment labels and region masks the reference's get_token_maps (utils/attention_utils.py:233-341) produces from
+    the maps its OWN plain pass captures (tiny XL config, same inputs as gen_xl_loops): pins the whole token-map path of
+    the product — on-device fp32 capture, averaging, resizes, the host clustering call — down to the label image."""
+    cfg = uo.tiny_xl_config()
+    S = 128
+    inp = synth_inputs(cfg, 3, S, 31)
+    ctx, te = inp["ctx"], inp["text_embeds"]
+    m = make_xl_sampler(ns, cfg, 2, (ctx[-1:], ctx[:1], te[-1:], te[:1]))
+    m.register_tokenmap_hooks()
+    m.sample(["x"], height=S * 8, width=S * 8, num_inference_steps=12, guidance_scale=8.5, negative_prompt=[""],
+             latents=inp["latents"].clone(), output_type="latent", run_rich_text=False)
+    au = ns.attention_utils
+    rec = {}
+    orig = au.SpectralClustering
+
+    class Recording(orig):
+        def fit_predict(self, X, y=None):
+            rec["affinity"] = np.array(X)
+            rec["labels"] = super().fit_predict(X, y)
+            return rec["labels"]
+
+    au.SpectralClustering = Recording
+    os.makedirs("/tmp/rtti_golden_tm", exist_ok=True)
+    obj = [torch.LongTensor([3]), torch.LongTensor([7, 8])]
+    try:
+        masks = au.get_token_maps(m.selfattn_maps, m.crossattn_maps, m.n_maps, "/tmp/rtti_golden_tm", S, S, obj, seed=6,
+                                  segment_threshold=0.3, num_segments=4)
+    finally:
+        au.SpectralClustering = orig
+    m.remove_tokenmap_hooks()
+    np.savez_compressed(os.path.join(GOLD, "xl_token_labels.npz"), labels=rec["labels"].reshape(32, 32).astype(np.int32),
+                        masks=torch.cat(masks)[:, 0].numpy(), affinity_rows=rec["affinity"][::64])
+    print("xl labels ok", np.bincount(rec["labels"]), [float(x.mean()) for x in masks])
+
+
 def synth_maps(seed):
     """Synthetic capture dicts with a clear 4-blob structure at 32x32 (+ a 16x16 layer that must be ignored)."""
     g = torch.Generator().manual_seed(seed)
@@ -290,13 +326,14 @@ def gen_token_maps(ns):
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ns = ref_shim.import_reference()
-    which = sys.argv[1:] or ["unet", "attention", "token_maps", "sd", "xl"]
+    which = sys.argv[1:] or ["unet", "attention", "token_maps", "sd", "xl", "xl_labels"]
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     if "unet" in which: gen_unet(ns)
     if "attention" in which: gen_attention(ns)
     if "token_maps" in which: gen_token_maps(ns)
     if "sd" in which: gen_sd_loops(ns)
     if "xl" in which: gen_xl_loops(ns)
+    if "xl_labels" in which: gen_xl_labels(ns)
 
 
 if __name__ == "__main__":

@@ -32,6 +32,8 @@ SIGNATURES = {
     "rtti_groupnorm_silu_fwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float, c_int, c_void_p]),
     "rtti_add_bias_f16": (c_int, [c_void_p] * 4 + [c_ll, c_int, c_void_p]),
     "rtti_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int, c_int, c_float, c_void_p]),
+    "rtti_add_bias_layernorm_fwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_float, c_void_p]),
+    "rtti_ff_geglu_fwd": (c_int, [c_void_p] * 4 + [c_ll, c_int, c_int, c_void_p]),
     "rtti_geglu_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "rtti_region_blend_cfg": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_int, c_ll, c_float, c_void_p,
                                       c_void_p, c_void_p, c_float, c_void_p]),

@@ -11,19 +11,22 @@
 //
 // Schedule of one CTA (128 query rows of one head; 5 warps: 0-3 softmax/epilogue, 4 = one control thread that issues
 // both the TMA loads and the MMAs):
-//   TMEM   S [0,64) fp32 scores of ONE 64-key tile, O_v [64 + 64 v, +64) fp32 accumulators  -> 128 / 256 / 512 columns
-//   smem   Q tile 16 KB | P tile 16 KB (fp16, K-major SWIZZLE_128B, also the output staging tile) | K ring 2 x 8 KB |
-//          V ring 2 x NV x 8 KB
+//   TMEM   S  fp32 scores of ONE 64-key tile (64 columns), P packed-fp16 probabilities (32 columns per buffer),
+//          O_v fp32 accumulators (64 columns per group member).
+//            plain  (NV = 1): two allocations, 128 (S, O) + 32 (P) columns -> THREE CTAs per SM (480 of 512 columns)
+//            groups (NV <= 6): one 512-column allocation: S | P0 | P1 | O_0..O_5 -> one CTA per SM
+//   smem   Q tile 16 KB (later the output staging tile) | K ring KST x 8 KB | V ring KST x NV x 8 KB
 //   * a softmax thread owns one query row: tcgen05.ld of its 64 scores, then IMMEDIATELY releases S (`s_free`), so the
-//     MMA warp issues Q K_{j+1}^T while the exponentials of tile j are still being evaluated (register double buffering:
-//     the look-ahead of a second S buffer without its TMEM columns);
-//   * P_j goes to shared memory in the UMMA K-major swizzled layout (8 x st.shared.v4 per row) and feeds P V as an SS MMA;
-//   * with 128 TMEM columns and 64 KB of shared memory THREE CTAs share an SM (NV = 1): 12 softmax warps keep the MUFU
-//     pipe busy across each other's TMEM-load / max / store phases (the previous schedule: 8 warps, 53 % XU utilisation);
+//     control thread issues Q K_{j+1}^T while the exponentials of tile j are still being evaluated (register double
+//     buffering: the look-ahead of a second S buffer without its TMEM columns);
+//   * P_j is written back to TMEM (tcgen05.st) and feeds P V as a TS MMA (A operand from TMEM): shared-memory
+//     bandwidth is spent on K and V only (a first version staged P in shared memory: 80 KB of smem traffic per tile,
+//     slower; profiles/r02_kernels_selfattn_psmem_first.jsonl);
+//   * groups double-buffer P, so the softmax of tile j+1 overlaps the NV P V_j MMAs (640 tensor cycles for 5 members);
 //   * no "stage empty" barriers: the control thread learns that Q K_j^T has completed from `s_free` (the softmax warps
 //     read S_j only after it) and that P V_{j-1} has completed from `p_full` (they write P_j only after it), so it
-//     refills the K stage of tile j with tile j+2 and the V stage of tile j-1 with tile j+1 at those points;
-//   * lazy rescale of O (only when a row max grows by more than 2^8) as before, on all NV accumulators.
+//     refills the K stage of tile j and the V stage of tile j-1 at those points;
+//   * lazy rescale of O (only when a row max grows by more than 2^8) on all NV accumulators.
 #include "ptx.cuh"
 #include "rtti_internal.h"
 
@@ -40,20 +43,21 @@ struct AttnSelfParams {
 
 namespace sa {
 constexpr int KT = 64;
-constexpr int KSTAGE = 2;
 constexpr int Q_TILE = 128 * 128;   // bytes
 constexpr int KV_TILE = KT * 128;   // 8 KB
 constexpr int THREADS = 160;
 template <int NV> struct Cfg {
+  static constexpr int KST = 3;                                // K / V ring depth
+  static constexpr int PBUF = NV == 1 ? 1 : 2;                 // P buffers in TMEM
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_P = OFF_Q + Q_TILE;
-  static constexpr int OFF_K = OFF_P + Q_TILE;
-  static constexpr int OFF_V = OFF_K + KSTAGE * KV_TILE;
-  static constexpr int OFF_BAR = OFF_V + KSTAGE * NV * KV_TILE;
-  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;   // + alignment slack
-  static constexpr uint32_t TMEM_COLS = (64 + 64 * NV) <= 128 ? 128 : ((64 + 64 * NV) <= 256 ? 256 : 512);
-  static constexpr int MIN_CTAS = NV == 1 ? 3 : (NV <= 3 ? 2 : 1);
-  static constexpr int MAX_REGS = NV == 1 ? 136 : (NV <= 3 ? 200 : 255);   // 65536 / (160 threads x MIN_CTAS), 8-register granules
+  static constexpr int OFF_K = OFF_Q + Q_TILE;
+  static constexpr int OFF_V = OFF_K + KST * KV_TILE;
+  static constexpr int OFF_BAR = OFF_V + KST * NV * KV_TILE;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;      // + alignment slack
+  static constexpr uint32_t COLS_A = NV == 1 ? 128 : 512;      // S, (P), O
+  static constexpr uint32_t COL_P = 64;                        // groups: P buffers at [64, 128)
+  static constexpr uint32_t COL_O = NV == 1 ? 64 : 128;
+  static constexpr int MAX_REGS = NV == 1 ? 136 : 255;         // 65536 / (160 threads x 3 CTAs), 8-register granules
 };
 }  // namespace sa
 
@@ -64,18 +68,22 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                  const __grid_constant__ AttnSelfParams p) {
   using namespace sa;
   using C = Cfg<NV>;
+  constexpr int KST = C::KST, PBUF = C::PBUF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // [2]
-  uint64_t* v_full = bars + 3;        // [2]
-  uint64_t* s_full = bars + 5;        // QK^T_j landed in TMEM
-  uint64_t* s_free = bars + 6;        // all 128 rows of S_j are in registers
-  uint64_t* p_full = bars + 7;        // P_j is in shared memory (and P V_{j-1} has completed)
-  uint64_t* pv_done = bars + 8;       // P V_j has completed (P tile reusable, O consistent)
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* k_full = bars + 1;        // [3]
+  uint64_t* v_full = bars + 4;        // [3]
+  uint64_t* s_full = bars + 7;        // QK^T_j landed in TMEM
+  uint64_t* s_free = bars + 8;        // all 128 rows of S_j are in registers
+  uint64_t* p_full = bars + 9;        // [2] P_j is in TMEM buffer j % PBUF. One barrier PER BUFFER: with two buffers the
+                                      // softmax warps may finish tile j+1 before the control warp has observed p_full(j)
+                                      // (it can sit in a v_full wait, e.g. cold L2) — on a single barrier the phase would
+                                      // flip twice and the parity wait would never return (seen as a hang after an L2 flush)
+  uint64_t* pv_done = bars + 11;      // [2] P V_j has completed (P buffer j % PBUF reusable, O consistent)
+  uint64_t* o_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);   // [2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -89,84 +97,98 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     if (lane == 0) {
       tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
       mbar_init(q_full, 1);
-      for (int i = 0; i < KSTAGE; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
-      mbar_init(s_full, 1); mbar_init(s_free, 128); mbar_init(p_full, 128); mbar_init(pv_done, 1); mbar_init(o_full, 1);
+      for (int i = 0; i < KST; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
+      mbar_init(s_full, 1); mbar_init(s_free, 128); mbar_init(&p_full[0], 128); mbar_init(&p_full[1], 128);
+      mbar_init(&pv_done[0], 1); mbar_init(&pv_done[1], 1); mbar_init(o_full, 1);
       mbar_fence_init();
     }
     __syncwarp();
-    tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    tmem_alloc_keep_permit<C::COLS_A>(&tmem_slot[0]);
+    if (NV == 1) tmem_alloc_keep_permit<32>(&tmem_slot[1]);
+    tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = tmem_slot[0];
+  const uint32_t tmem_p = NV == 1 ? tmem_slot[1] : tmem + C::COL_P;   // groups: buffer b at tmem_p + 32 b
+  const uint32_t tmem_o = tmem + C::COL_O;
 
   if (warp == 4) {
-    // ------------------------------------------------------------- control thread: TMA loads + MMA issue
-    if (lane == 0) {
-      constexpr uint32_t IDESC_QK = umma_idesc_f16(128, KT, 0, 0);
-      constexpr uint32_t IDESC_PV = umma_idesc_f16(128, 64, 0, 1);
-      const uint32_t smem_base = smem_u32(smem);
-      auto load_k = [&](int j) {
-        const int st = j % KSTAGE;
-        mbar_expect_tx(&k_full[st], KV_TILE);
-        tma_load_4d(smem + C::OFF_K + st * KV_TILE, &tm_k, &k_full[st], 0, h, j * KT, b_qk);
-      };
-      auto load_v = [&](int j) {
-        const int st = j % KSTAGE;
-        mbar_expect_tx(&v_full[st], nv * KV_TILE);
-        for (int v = 0; v < nv; ++v)
-          tma_load_4d(smem + C::OFF_V + (st * NV + v) * KV_TILE, &tm_v, &v_full[st], 0, h, j * KT, p.vent[grp][v]);
-      };
-      auto issue_qk = [&](int j) {
-        const int st = j % KSTAGE;
-        mbar_wait(&k_full[st], (j / KSTAGE) & 1);
-        tc_fence_after();
-        for (int kk = 0; kk < p.ksteps_qk; ++kk) {
-          const uint64_t da = umma_desc_sw128(smem_base + C::OFF_Q + kk * 32, 0, 1024);
-          const uint64_t db = umma_desc_sw128(smem_base + C::OFF_K + st * KV_TILE + kk * 32, 0, 1024);
-          mma_f16_ss(tmem, da, db, IDESC_QK, kk > 0);
-        }
-        tc_commit(s_full);
-      };
-      mbar_expect_tx(q_full, Q_TILE);
-      tma_load_4d(smem + C::OFF_Q, &tm_q, q_full, 0, h, q0, b_qk);
-      load_k(0);
-      if (nt > 1) load_k(1);
-      load_v(0);
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < nt; ++j) {
-        if (j + 1 < nt) {
-          mbar_wait(s_free, j & 1);       // Q K_j^T has completed and S_j lives in the softmax warps' registers
-          tc_fence_after();
-          issue_qk(j + 1);
-          if (j + 2 < nt) load_k(j + 2);  // into the stage of K_j
-        }
-        const int st = j % KSTAGE;
-        mbar_wait(&v_full[st], (j / KSTAGE) & 1);
-        mbar_wait(p_full, j & 1);         // P_j written; the softmax warps saw pv_done(j-1) before writing it
-        tc_fence_after();
-        if (j + 1 < nt) load_v(j + 1);    // into the stage of V_{j-1}
-        for (int v = 0; v < nv; ++v) {
+    // ------------------------------------------------------------- control warp: TMA loads + MMA issue.
+    // All 32 lanes run the loop (uniform control flow, operands in uniform registers); `el` predicates the issue.
+    const uint32_t el = elect_one() ? 1u : 0u;
+    constexpr uint32_t IDESC_QK = umma_idesc_f16(128, KT, 0, 0);
+    constexpr uint32_t IDESC_PV = umma_idesc_f16(128, 64, 0, 1);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t dq0 = umma_desc_sw128(smem_base + C::OFF_Q, 0, 1024);
+    const uint64_t dk0 = umma_desc_sw128(smem_base + C::OFF_K, 0, 1024);
+    const uint64_t dv0 = umma_desc_sw128(smem_base + C::OFF_V, KV_TILE, 1024);
+    int vent[NV];
 #pragma unroll
-          for (int kk = 0; kk < KT / 16; ++kk) {
-            const uint64_t da = umma_desc_sw128(smem_base + C::OFF_P + kk * 32, 0, 1024);
-            const uint64_t db = umma_desc_sw128(smem_base + C::OFF_V + (st * NV + v) * KV_TILE + kk * 2048, KV_TILE, 1024);
-            mma_f16_ss(tmem + 64u + 64u * v, da, db, IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
-          }
-        }
-        tc_commit(pv_done);
-        if (j == nt - 1) tc_commit(o_full);
+    for (int v = 0; v < NV; ++v) vent[v] = p.vent[grp][v < nv ? v : 0];
+    auto load_k = [&](int j) {
+      const int st = j % KST;
+      mbar_expect_tx_p(&k_full[st], KV_TILE, el);
+      tma_load_4d_p(smem_base + C::OFF_K + st * KV_TILE, &tm_k, &k_full[st], 0, h, j * KT, b_qk, el);
+    };
+    auto load_v = [&](int j) {
+      const int st = j % KST;
+      mbar_expect_tx_p(&v_full[st], nv * KV_TILE, el);
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        if (v < nv) tma_load_4d_p(smem_base + C::OFF_V + (st * NV + v) * KV_TILE, &tm_v, &v_full[st], 0, h, j * KT, vent[v], el);
+    };
+    auto issue_qk = [&](int j) {
+      const int st = j % KST;
+      mbar_wait(&k_full[st], (j / KST) & 1);
+      tc_fence_after();
+      const uint64_t dk = dk0 + static_cast<uint64_t>((st * KV_TILE) >> 4);
+      for (int kk = 0; kk < p.ksteps_qk; ++kk)
+        mma_f16_ss_p(tmem, dq0 + 2 * kk, dk + 2 * kk, IDESC_QK, kk > 0, el);   // +32 bytes per 16-element k step
+      tc_commit_p(s_full, el);
+    };
+    mbar_expect_tx_p(q_full, Q_TILE, el);
+    tma_load_4d_p(smem_base + C::OFF_Q, &tm_q, q_full, 0, h, q0, b_qk, el);
+    for (int j = 0; j < KST && j < nt; ++j) load_k(j);
+    for (int j = 0; j < KST - 1 && j < nt; ++j) load_v(j);
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < nt; ++j) {
+      if (j + 1 < nt) {
+        mbar_wait(s_free, j & 1);           // Q K_j^T has completed and S_j lives in the softmax warps' registers
+        tc_fence_after();
+        issue_qk(j + 1);
+        if (j + KST < nt) load_k(j + KST);  // into the stage of K_j
       }
+      const int st = j % KST;
+      mbar_wait(&v_full[st], (j / KST) & 1);
+      mbar_wait(&p_full[j % PBUF], (j / PBUF) & 1);   // P_j written; the softmax warps saw P V_{j-PBUF} complete before writing it
+      tc_fence_after();
+      // the V stage of tile j-1 is free once P V_{j-1} has completed: known from p_full(j) with one P buffer; with two
+      // buffers p_full(j) only implies P V_{j-2}, so the refill trails by one more tile
+      if (PBUF == 1) { if (j + KST - 1 < nt) load_v(j + KST - 1); }
+      else if (j >= 1 && j + KST - 2 < nt) load_v(j + KST - 2);
+      const uint32_t pa = tmem_p + 32u * (j % PBUF);
+      const uint64_t dvs = dv0 + static_cast<uint64_t>((st * NV * KV_TILE) >> 4);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (v < nv) {
+#pragma unroll
+          for (int kk = 0; kk < KT / 16; ++kk)   // V is MN-major: 16 keys further = +2048 bytes
+            mma_f16_ts_p(tmem_o + 64u * v, pa + kk * 8, dvs + ((v * KV_TILE + kk * 2048) >> 4), IDESC_PV,
+                         (j > 0 || kk > 0) ? 1u : 0u, el);
+        }
+      }
+      tc_commit_p(&pv_done[j % PBUF], el);
+      if (j == nt - 1) tc_commit_p(o_full, el);
     }
   } else {
     // ------------------------------------------------------------- softmax + epilogue: thread == query row == TMEM lane
     const int row = warp * 32 + lane;
-    const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t tlane = tmem + lane_off;
     const bool row_ok = (q0 + row) < p.n_q;
-    uint8_t* prow = smem + C::OFF_P + row * 128;
-    const int sw = row & 7;
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
     float m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < nt; ++j) {
@@ -189,52 +211,53 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
       for (int i = 1; i < KT; ++i) mx = fmaxf(mx, s[i]);
       const float mxs = mx * p.scale_log2;
-      if (j > 0) {   // P tile and (for a rescale) the O accumulators are free once P V_{j-1} has completed
-        mbar_wait(pv_done, (j - 1) & 1);
-        tc_fence_after();
-      }
       if (j == 0) {
         m_ref = mxs;
       } else {
         const bool need = mxs > m_ref + 8.f;   // lazy rescale: keeps P <= 2^8 in fp16
         if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(&pv_done[(j - 1) % PBUF], ((j - 1) / PBUF) & 1);   // O is being accumulated by P V_{j-1}
+          tc_fence_after();
           const float alpha = need ? ex2_approx(m_ref - mxs) : 1.f;
           if (need) m_ref = mxs;
           l *= alpha;
           for (int c = 0; c < 4 * nv; ++c) {
             uint32_t o[16];
-            tmem_ld16(tlane + 64u + 16 * c, o);
+            tmem_ld16(tmem_o + lane_off + 16 * c, o);
             tmem_wait_ld_regs16(o);
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tlane + 64u + 16 * c, o);
+            tmem_st16(tmem_o + lane_off + 16 * c, o);
           }
-          tmem_wait_st();
         }
       }
+      const uint32_t tp = tmem_p + lane_off + 32u * (j % PBUF);
       const float2 nm2 = make_float2(-m_ref, -m_ref);
       float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+      uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {   // 8 keys -> one 16-byte chunk of the swizzled P row
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 x = fma_f32x2(make_float2(s[8 * c + 2 * i], s[8 * c + 2 * i + 1]), sc2, nm2);
-          const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-          if (i & 1) acc1 = add_f32x2(acc1, e); else acc0 = add_f32x2(acc0, e);
-          w[i] = pack_half2(e.x, e.y);
-        }
-        *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      for (int i = 0; i < 32; ++i) {
+        const float2 x = fma_f32x2(make_float2(s[2 * i], s[2 * i + 1]), sc2, nm2);
+        const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+        if (i & 1) acc1 = add_f32x2(acc1, e); else acc0 = add_f32x2(acc0, e);
+        pk[i] = pack_half2(e.x, e.y);
       }
+      if (j >= PBUF) {   // the P buffer of this tile was last read by P V_{j-PBUF}: waited for AFTER the exponentials,
+        mbar_wait(&pv_done[j % PBUF], ((j / PBUF) - 1) & 1);   // when that MMA has long completed
+        tc_fence_after();
+      }
+      tmem_st32(tp, pk);
       l += (acc0.x + acc0.y) + (acc1.x + acc1.y);
-      fence_proxy_async_smem();
+      tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[j % PBUF]);
     }
-    // ---- epilogue: O_v / l -> fp16 -> swizzled staging tile (the P tile) -> TMA store, one member at a time
+    // ---- epilogue: O_v / l -> fp16 -> swizzled staging tile (the Q tile, dead by now) -> TMA store, one member at a time
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv_l = 1.f / l;
+    uint8_t* orow = smem + C::OFF_Q + row * 128;
+    const int sw = row & 7;
     for (int v = 0; v < nv; ++v) {
       if (v > 0) {
         if (threadIdx.x == 0) tma_store_wait_read();   // the previous member's store has drained the staging tile
@@ -243,7 +266,7 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t o[32];
-        tmem_ld32(tlane + 64u + 64u * v + 32 * hh, o);
+        tmem_ld32(tmem_o + lane_off + 64u * v + 32 * hh, o);
         tmem_wait_ld_regs32(o);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -252,7 +275,7 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           w.y = pack_half2(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l);
           w.z = pack_half2(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l);
           w.w = pack_half2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(prow + (((hh * 4 + q) ^ sw) << 4)) = w;
+          *reinterpret_cast<uint4*>(orow + (((hh * 4 + q) ^ sw) << 4)) = w;
         }
       }
       tc_fence_before();
@@ -260,7 +283,7 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
       const int b = p.vent[grp][v];
       if (threadIdx.x == 0) {
-        tma_store_4d(&tm_o, smem + C::OFF_P, 0, h, q0, b);
+        tma_store_4d(&tm_o, smem + C::OFF_Q, 0, h, q0, b);
         tma_store_commit();
       }
       if (p.lse != nullptr && row_ok)
@@ -270,7 +293,10 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<C::TMEM_COLS>(tmem);
+  if (warp == 4) {
+    tmem_dealloc<C::COLS_A>(tmem);
+    if (NV == 1) tmem_dealloc<32>(tmem_p);
+  }
 }
 
 template <int NV>
@@ -285,8 +311,25 @@ static int launch_class(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
   return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
 }
 
-// Entries are grouped by their score source; groups of 1 / 2-3 / 4-6 members go to the 128 / 256 / 512-column kernel
-// (larger groups are split). One launch per class that occurs (at most three), heaviest class first.
+// Library-owned side stream + fork/join events, one set per device (created on first use, never destroyed).
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+static SideStream* side_stream() {
+  static SideStream per_dev[16];
+  static bool ready[16] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!ready[dev]) {
+    SideStream& s = per_dev[dev];
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ready[dev] = true;
+  }
+  return &per_dev[dev];
+}
+
+// Entries are grouped by their score source; single entries go to the 3-CTA/SM plain kernel, groups of 2..6 members to
+// the 512-column group kernel (larger groups are split into balanced chunks). At most two launches, groups first.
 int launch_attn_self(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                      int batch, int heads, int head_dim, int n_q, int n_k, float scale_log2, const int8_t* qk_src,
                      float* lse, int max_group, cudaStream_t stream) {
@@ -298,8 +341,8 @@ int launch_attn_self(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   base.lse = lse;
   if (max_group < 1) max_group = 1;
   if (max_group > 6) max_group = 6;
-  AttnSelfParams cls[3] = {base, base, base};   // NV = 1, 3, 6
-  int n[3] = {0, 0, 0};
+  AttnSelfParams cls[2] = {base, base};   // plain, groups
+  int n[2] = {0, 0};
   for (int s = 0; s < batch; ++s) {
     int members[64], m = 0;
     for (int b = 0; b < batch; ++b)
@@ -308,7 +351,7 @@ int launch_attn_self(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
     const int chunks = (m + max_group - 1) / max_group;   // balanced split of groups larger than max_group
     for (int c = 0, off = 0; c < chunks; ++c) {
       const int take = m / chunks + (c < m % chunks ? 1 : 0);
-      const int k = take == 1 ? 0 : (take <= 3 ? 1 : 2);
+      const int k = take == 1 ? 0 : 1;
       AttnSelfParams& q = cls[k];
       const int g = n[k]++;
       if (g >= 64) return RTTI_ERR_ARG;
@@ -318,8 +361,23 @@ int launch_attn_self(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
     }
   }
   int rc = RTTI_OK;
-  if (n[2] && (rc = launch_class<6>(tq, tk, tv, to, cls[2], n[2], stream)) != RTTI_OK) return rc;
-  if (n[1] && (rc = launch_class<3>(tq, tk, tv, to, cls[1], n[1], stream)) != RTTI_OK) return rc;
+  if (n[1] && n[0]) {
+    // Both classes occur (an injection step): run them CONCURRENTLY. Each has a poor tail on its own (a group CTA owns a
+    // whole SM: 160 / 320 CTAs on 148 SMs at the 32^2 / 64^2 level; the plain kernel 480 / 960 CTAs on 444 slots), and the
+    // block scheduler starts the second kernel's CTAs as soon as the first one has none left to dispatch, so each
+    // kernel's last wave is filled by the other. Fork / join through events on a library-owned side stream: capturable
+    // into a CUDA graph (the events become graph edges), no host synchronisation.
+    SideStream* ss = side_stream();
+    if (ss == nullptr) return RTTI_ERR_CUDA;
+    if (cudaEventRecord(ss->fork, stream) != cudaSuccess || cudaStreamWaitEvent(ss->stream, ss->fork, 0) != cudaSuccess)
+      return RTTI_ERR_CUDA;
+    if ((rc = launch_class<6>(tq, tk, tv, to, cls[1], n[1], stream)) != RTTI_OK) return rc;
+    if ((rc = launch_class<1>(tq, tk, tv, to, cls[0], n[0], ss->stream)) != RTTI_OK) return rc;
+    if (cudaEventRecord(ss->join, ss->stream) != cudaSuccess || cudaStreamWaitEvent(stream, ss->join, 0) != cudaSuccess)
+      return RTTI_ERR_CUDA;
+    return RTTI_OK;
+  }
+  if (n[1] && (rc = launch_class<6>(tq, tk, tv, to, cls[1], n[1], stream)) != RTTI_OK) return rc;
   if (n[0] && (rc = launch_class<1>(tq, tk, tv, to, cls[0], n[0], stream)) != RTTI_OK) return rc;
   return rc;
 }

@@ -229,6 +229,68 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __r
   }
 }
 
+// ============================================================================ residual + bias + LayerNorm
+// h = fp16(a + resid + bias[c]);  y = LayerNorm(h) * gamma + beta      (attention.py:155-181: `attn(...) + hidden_states`
+// followed by the next norm). One pass over DRAM: reads a and resid, writes h (may alias resid) and y. The statistics
+// are taken on the fp16-rounded h, i.e. on exactly the tensor later layers read.
+template <int VPL>
+__global__ void add_bias_layernorm_kernel(const __half* __restrict__ a, const __half* resid,
+                                          const __half* __restrict__ bias, const __half* __restrict__ gamma,
+                                          const __half* __restrict__ beta, __half* h_out, __half* __restrict__ y,
+                                          int rows, int c, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = c / 8;
+  const size_t off = (size_t)warp * c;
+  Half8 ra[VPL], rr[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+    if (lane + 32 * k < nvec) {
+      ra[k] = *reinterpret_cast<const Half8*>(a + off + (lane + 32 * k) * 8);
+      rr[k] = *reinterpret_cast<const Half8*>(resid + off + (lane + 32 * k) * 8);
+    }
+  float f[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec) {
+      float fa[8], fr[8], fb[8];
+      unpack8(ra[k], fa);
+      unpack8(rr[k], fr);
+      if (bias != nullptr) unpack8(*reinterpret_cast<const Half8*>(bias + v * 8), fb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[k][i] = fa[i] + fr[i] + (bias != nullptr ? fb[i] : 0.f);
+      const Half8 hv = pack8(f[k]);
+      *reinterpret_cast<Half8*>(h_out + off + v * 8) = hv;
+      unpack8(hv, f[k]);   // the rounded values
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += f[k][i];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)c;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+    if (lane + 32 * k < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[k][i] - mean; sq += d * d; }
+    }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)c + eps);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec) {
+      float ga[8], be[8], o[8];
+      unpack8(*reinterpret_cast<const Half8*>(gamma + v * 8), ga);
+      unpack8(*reinterpret_cast<const Half8*>(beta + v * 8), be);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * ga[i] + be[i];
+      *reinterpret_cast<Half8*>(y + off + v * 8) = pack8(o);
+    }
+  }
+}
+
 // ============================================================================ GEGLU
 __global__ void geglu_kernel(const __half* __restrict__ proj, __half* __restrict__ y, long long rows, int inner) {
   const int nvec = inner / 8;
@@ -458,6 +520,25 @@ extern "C" int rtti_layernorm_fwd(const void* x, const void* gamma, const void* 
   if (vpl <= 1) LN(1); else if (vpl <= 2) LN(2); else if (vpl <= 3) LN(3); else if (vpl <= 4) LN(4);
   else if (vpl <= 5) LN(5); else if (vpl <= 6) LN(6); else LN(8);
 #undef LN
+  return ok_or_cuda();
+}
+
+extern "C" int rtti_add_bias_layernorm_fwd(const void* a, const void* resid, const void* bias, const void* gamma,
+                                           const void* beta, void* h_out, void* y, int rows, int c, float eps,
+                                           void* stream) {
+  if (!a || !resid || !gamma || !beta || !h_out || !y) return RTTI_ERR_ARG;
+  if (rows < 1) return RTTI_ERR_ARG;
+  if (c % 8 != 0 || c > 8 * 32 * 8) return RTTI_ERR_SHAPE;
+  if (((uintptr_t)a | (uintptr_t)resid | (uintptr_t)bias | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)h_out | (uintptr_t)y) & 15)
+    return RTTI_ERR_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vpl = (c / 8 + 31) / 32;
+  const int blocks = (rows + 7) / 8;
+#define ALN(V) add_bias_layernorm_kernel<V><<<blocks, 256, 0, st>>>((const __half*)a, (const __half*)resid, (const __half*)bias, \
+    (const __half*)gamma, (const __half*)beta, (__half*)h_out, (__half*)y, rows, c, eps)
+  if (vpl <= 1) ALN(1); else if (vpl <= 2) ALN(2); else if (vpl <= 3) ALN(3); else if (vpl <= 4) ALN(4);
+  else if (vpl <= 5) ALN(5); else if (vpl <= 6) ALN(6); else ALN(8);
+#undef ALN
   return ok_or_cuda();
 }
 

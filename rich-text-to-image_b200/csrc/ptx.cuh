@@ -85,13 +85,21 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 // ------------------------------------------------------------------ tcgen05 / TMEM
+// A CTA may allocate several times, but not after it has relinquished its allocation permit.
 template <uint32_t kCols>
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // whole warp
+__device__ __forceinline__ void tmem_alloc_keep_permit(uint32_t* smem_result) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
                    smem_u32(smem_result)),
                "n"(kCols)
                : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {  // whole warp, after the CTA's last allocation
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // whole warp; the CTA's only allocation
+  tmem_alloc_keep_permit<kCols>(smem_result);
+  tmem_relinquish();
 }
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp
@@ -199,6 +207,59 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
       "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
+}
+
+// ------------------------------------------------------------------ predicated issue (warp-uniform control warps)
+// A control warp that runs its loop with ALL lanes and predicates only the issuing instructions keeps descriptors and
+// addresses in uniform registers; issuing from inside `if (lane == 0)` makes the compiler wrap every tcgen05 / TMA
+// operand in R2UR + ELECT + BRA.U.ANY sequences (measured: ~1000 SASS instructions per key tile in the 6-member
+// group kernel, which made the single issuing thread the bottleneck). `el` = 1 on the elected lane, 0 elsewhere.
+__device__ __forceinline__ void mbar_expect_tx_p(uint64_t* bar, uint32_t bytes, uint32_t el) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+               "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)), "r"(bytes), "r"(el)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_p(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                              int c2, int c3, uint32_t el) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+               "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+               " [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}\n" ::"r"(smem_dst),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(el)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_p(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                              uint32_t el) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+               "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+               " [%0], [%1, {%3, %4}], [%2];\n\t}\n" ::"r"(smem_dst),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(el)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_commit_p(uint64_t* bar, uint32_t el) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)),
+               "r"(el)
+               : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate, uint32_t el) {
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+               "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+               "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(el)
+               : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate, uint32_t el) {
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+               "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+               "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(el)
+               : "memory");
 }
 
 // ------------------------------------------------------------------ UMMA descriptors

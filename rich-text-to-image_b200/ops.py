@@ -14,6 +14,9 @@ _F16 = torch.float16
 
 # number of kernels of librtti_b200.so launched since import (bench.py reports the count of a timed region)
 LAUNCHES = 0
+# feed-forward input projection: True = rtti_ff_geglu_fwd (hand-written tcgen05 GEMM with the gate in its epilogue),
+# False = cuBLAS GEMM + rtti_geglu_fwd (kept for A/B measurements, profiles/)
+FUSED_FF_GEGLU = True
 # when a list: attention() appends (start_event, end_event, kind, flops, algorithmic_bytes) per launch
 PROFILE = None
 
@@ -158,6 +161,42 @@ def layernorm(x, gamma, beta, eps, out=None):
         out = torch.empty_like(x)
     _lib.check(lib.rtti_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, C, float(eps), _stream()),
                "rtti_layernorm_fwd")
+    _count(1)
+    return out
+
+
+def add_bias_layernorm(a, resid, bias, gamma, beta, eps, h_out=None, y=None):
+    """h = a + resid + bias[c] (fp16, may be written over `resid`), y = LayerNorm(h) (rtti_add_bias_layernorm_fwd).
+    Returns (h, y)."""
+    lib = _lib.load()
+    _req(a, _F16, "a"); _req(resid, _F16, "resid"); _req(gamma, _F16, "gamma"); _req(beta, _F16, "beta")
+    assert a.is_contiguous() and resid.is_contiguous() and a.shape == resid.shape
+    C = a.shape[-1]
+    rows = a.numel() // C
+    if h_out is None:
+        h_out = resid
+    if y is None:
+        y = torch.empty_like(a)
+    _lib.check(lib.rtti_add_bias_layernorm_fwd(_ptr(a), _ptr(resid), _ptr(bias), _ptr(gamma), _ptr(beta), _ptr(h_out), _ptr(y),
+                                               rows, C, float(eps), _stream()), "rtti_add_bias_layernorm_fwd")
+    _count(1)
+    return h_out, y
+
+
+def ff_geglu(x, weight, bias=None, out=None):
+    """(x W_v^T + b_v) * gelu(x W_g^T + b_g) with weight [2n, k] = [W_v; W_g] (rtti_ff_geglu_fwd: tcgen05 GEMM with the
+    gate in the epilogue). x [..., k] fp16 contiguous -> [..., n]."""
+    lib = _lib.load()
+    _req(x, _F16, "x"); _req(weight, _F16, "weight")
+    assert x.is_contiguous() and weight.is_contiguous() and weight.shape[1] == x.shape[-1]
+    k = x.shape[-1]
+    n = weight.shape[0] // 2
+    m = x.numel() // k
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (n,), dtype=_F16, device=x.device)
+    if bias is not None:
+        _req(bias, _F16, "bias"); assert bias.is_contiguous() and bias.numel() == 2 * n
+    _lib.check(lib.rtti_ff_geglu_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(out), m, n, k, _stream()), "rtti_ff_geglu_fwd")
     _count(1)
     return out
 

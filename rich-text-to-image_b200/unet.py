@@ -223,11 +223,15 @@ class BasicTransformerBlock(nn.Module):
         self.ff.net = nn.ModuleList([nn.Module(), nn.Identity(), nn.Linear(dim * 4, dim)])
         self.ff.net[0].proj = nn.Linear(dim, dim * 8)
 
-    def forward(self, h, ctx, ctrl: RegionControl, name):
+    def forward(self, h, n, ctx, ctrl: RegionControl, name):
+        """h: residual stream [B, T, C]; n = norm1(h), already evaluated (fused into the previous block's last
+        residual add). Returns (h, a, bias): the stream BEFORE the feed-forward residual add, the feed-forward output
+        without its bias, and that bias — the caller fuses `h + a + bias` with whatever norm comes next.
+        Every `x + sublayer(x)` of attention.py:155-204 is one rtti_add_bias_layernorm_fwd call together with the
+        LayerNorm that follows it (the projections run without their bias epilogue)."""
         B, T, C = h.shape
         heads = self.attn1.heads
         # ---- self-attention (attention.py:150-160)
-        n = self.norm1(h)
         qkv = F.linear(n, self.attn1.fused_weight())
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         cap = ctrl.capture
@@ -237,9 +241,9 @@ class BasicTransformerBlock(nn.Module):
         if tgt is not None:
             r = ctrl.capture_row
             ops.attn_probs_mean_accum(q[r], k[r], lse[r], tgt[0], heads)
-        h = F.linear(o, self.attn1.to_out[0].weight, self.attn1.to_out[0].bias).add_(h)
+        a = F.linear(o, self.attn1.to_out[0].weight)
+        h, n = ops.add_bias_layernorm(a, h, self.attn1.to_out[0].bias, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         # ---- cross-attention (attention.py:163-178)
-        n = self.norm2(h)
         q = F.linear(n, self.attn2.to_q.weight)
         kv = None
         key = name + ".attn2"
@@ -258,12 +262,15 @@ class BasicTransformerBlock(nn.Module):
                 slots[ctrl.capture_row] = 0
         o = ops.attention(q, ck, cv, heads, word_pos=ctrl.word_pos, font_size=ctrl.font_size,
                           fs_batch_mask=ctrl.fs_batch_mask, pbar_accum=pbar, cap_slot=slots)
-        h = F.linear(o, self.attn2.to_out[0].weight, self.attn2.to_out[0].bias).add_(h)
+        a = F.linear(o, self.attn2.to_out[0].weight)
+        h, n = ops.add_bias_layernorm(a, h, self.attn2.to_out[0].bias, self.norm3.weight, self.norm3.bias, self.norm3.eps)
         # ---- feed-forward with GEGLU (attention.py:181-204, 283-304)
-        n = self.norm3(h)
-        p = F.linear(n, self.ff.net[0].proj.weight, self.ff.net[0].proj.bias)
-        g = ops.geglu(p)
-        return F.linear(g, self.ff.net[2].weight, self.ff.net[2].bias).add_(h)
+        proj = self.ff.net[0].proj
+        if ops.FUSED_FF_GEGLU and C % 64 == 0:
+            g = ops.ff_geglu(n, proj.weight, proj.bias)     # GEMM + bias + gate in one kernel; no [B, T, 8C] intermediate
+        else:
+            g = ops.geglu(F.linear(n, proj.weight, proj.bias))
+        return h, F.linear(g, self.ff.net[2].weight), self.ff.net[2].bias
 
 
 class Transformer2DModel(nn.Module):
@@ -287,9 +294,18 @@ class Transformer2DModel(nn.Module):
         # channels-last already: the permutes of transformer_2d.py:274-283, 299-307 are no-ops here
         h = self.norm(x, silu=False)
         h = self._proj(self.proj_in, h)
-        for i, blk in enumerate(self.transformer_blocks):
-            h = blk(h, ctx, ctrl, f"{name}.transformer_blocks.{i}")
-        return self._proj(self.proj_out, h).add_(x)
+        blocks = self.transformer_blocks
+        n = blocks[0].norm1(h)
+        for i, blk in enumerate(blocks):
+            h, a, bias = blk(h, n, ctx, ctrl, f"{name}.transformer_blocks.{i}")
+            if i + 1 < len(blocks):   # feed-forward residual add + the next block's norm1 in one pass
+                nxt = blocks[i + 1].norm1
+                h, n = ops.add_bias_layernorm(a, h, bias, nxt.weight, nxt.bias, nxt.eps)
+            else:
+                h = ops.add_bias_f16(h, a, bias, out=a)
+        w = self.proj_out.weight if self.use_linear_projection else self.proj_out.weight.view(self.proj_out.weight.shape[0], -1)
+        y = F.linear(h, w)
+        return ops.add_bias_f16(x, y, self.proj_out.bias, out=y)   # proj_out bias + transformer residual (transformer_2d.py:310)
 
 
 class ResnetBlock2D(nn.Module):

@@ -133,6 +133,17 @@ def case_elementwise():
         y = ops.layernorm(x, ga, be, 1e-5)
         ref = torch.nn.functional.layer_norm(x.float(), (C,), ga.float(), be.float(), 1e-5)
         ok &= report(f"layernorm rows{rows} C{C}", y, ref, 4e-3, 1e-2)
+    for (rows, C) in [(4096, 640), (1024, 1280), (77, 320), (5, 2048), (64, 32)]:
+        a = torch.randn(rows, C, device="cuda").half(); r = (torch.randn(rows, C, device="cuda") * 2).half()
+        bi = torch.randn(C, device="cuda").half(); ga = torch.randn(C, device="cuda").half(); be = torch.randn(C, device="cuda").half()
+        for bias in (bi, None):
+            h_ref = (a.float() + r.float() + (bias.float() if bias is not None else 0)).half()
+            y_ref = torch.nn.functional.layer_norm(h_ref.float(), (C,), ga.float(), be.float(), 1e-5)
+            r2 = r.clone()
+            h, y = ops.add_bias_layernorm(a, r2, bias, ga, be, 1e-5)
+            assert h.data_ptr() == r2.data_ptr()
+            ok &= report(f"add_bias_layernorm h rows{rows} C{C} bias={bias is not None}", h, h_ref, 2e-3, 1e-3)
+            ok &= report(f"add_bias_layernorm y rows{rows} C{C} bias={bias is not None}", y, y_ref, 4e-3, 1e-2)
     for (rows, inner) in [(4096, 2560), (1024, 5120), (77, 128)]:
         pr = torch.randn(rows, 2 * inner, device="cuda").half()
         y = ops.geglu(pr)
@@ -169,8 +180,27 @@ def case_elementwise():
     return ok
 
 
+def case_ff_geglu():
+    """tcgen05 GEMM with the GEGLU gate in the epilogue against torch (fp32 matmul of the fp16 operands)."""
+    import torch
+    from rtti_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    ok = True
+    for (M, C, bias) in [(128, 64, True), (256, 128, False), (300, 320, True), (4096, 640, True), (8192, 1280, True), (77, 640, True)]:
+        x = torch.randn(M, C, device="cuda", generator=g).half()
+        w = (torch.randn(8 * C, C, device="cuda", generator=g) / C ** 0.5).half()
+        b = (0.3 * torch.randn(8 * C, device="cuda", generator=g)).half() if bias else None
+        y = ops.ff_geglu(x, w, b)
+        torch.cuda.synchronize()
+        pr = x.float() @ w.float().t() + (b.float() if b is not None else 0)
+        ref = pr[:, :4 * C] * torch.nn.functional.gelu(pr[:, 4 * C:])
+        ok &= report(f"ff_geglu M{M} C{C} bias={bias}", y, ref, 3e-3, 1e-2)
+    return ok
+
+
 CASES = {
     "elementwise": case_elementwise,
+    "ff_geglu": case_ff_geglu,
     "cross_small": lambda: attn_case(1, 1, 64, 128, 77),
     "cross_basic": lambda: attn_case(2, 4, 64, 256, 77),
     "self_1tile": lambda: attn_case(1, 1, 64, 128, 128),

@@ -91,6 +91,18 @@ def main():
             report(f"attn_probs_mean {tag}", sec, nbytes=8 * T * T + 4 * T * C, flops=2.0 * H * T * T * 64, bound="tensor")
     if os.environ.get("RTTI_KBENCH_ONLY") == "self":
         return
+    if os.environ.get("RTTI_KBENCH_ONLY") == "geglu":
+        for (rows, C) in ((B * 4096, 640), (B * 1024, 1280)):
+            x = rn(rows, C); w = (rn(8 * C, C).float() / C ** 0.5).half(); bb = rn(8 * C)
+            yo = torch.empty(rows, 4 * C, device="cuda", dtype=torch.float16)
+            fl = 2.0 * rows * C * 8 * C
+            sec = timeit(lambda: ops.ff_geglu(x, w, bb, out=yo))
+            report(f"ff_geglu (tcgen05 GEMM + gate epilogue) rows{rows} C{C}", sec, flops=fl, bound="tensor")
+            sec = timeit(lambda: ops.geglu(torch.nn.functional.linear(x, w, bb), out=yo))
+            report(f"cuBLAS linear + geglu kernel rows{rows} C{C}", sec, flops=fl, bound="tensor")
+            sec = timeit(lambda: torch.nn.functional.linear(x, w, bb))
+            report(f"cuBLAS linear only rows{rows} C{C}", sec, flops=fl, bound="tensor")
+        return
     for (HW, C) in ((16384, 320), (4096, 640), (4096, 1920), (1024, 1280), (1024, 2560)):
         x = rn(B, HW, C); ga, be = rn(C), rn(C); y = torch.empty_like(x); tb = rn(B, C)
         sec = timeit(lambda: ops.groupnorm_silu(x, ga, be, 32, 1e-5, True, chan_bias=tb, out=y))
@@ -102,6 +114,16 @@ def main():
         pr = rn(rows, 8 * C); yo = torch.empty(rows, 4 * C, device="cuda", dtype=torch.float16)
         sec = timeit(lambda: ops.geglu(pr, out=yo))
         report(f"geglu rows{rows} inner{4 * C}", sec, nbytes=2 * (pr.numel() + yo.numel()))
+    for (rows, C) in ((B * 4096, 640), (B * 1024, 1280)):   # feed-forward input projection of the two SDXL levels
+        x = rn(rows, C); w = (rn(8 * C, C).float() / C ** 0.5).half(); bb = rn(8 * C)
+        yo = torch.empty(rows, 4 * C, device="cuda", dtype=torch.float16)
+        fl = 2.0 * rows * C * 8 * C
+        sec = timeit(lambda: ops.ff_geglu(x, w, bb, out=yo))
+        report(f"ff_geglu (tcgen05 GEMM + gate epilogue) rows{rows} C{C}", sec, flops=fl, bound="tensor")
+        sec = timeit(lambda: ops.geglu(torch.nn.functional.linear(x, w, bb), out=yo))
+        report(f"cuBLAS linear + geglu kernel rows{rows} C{C}", sec, flops=fl, bound="tensor")
+        sec = timeit(lambda: torch.nn.functional.linear(x, w, bb))
+        report(f"cuBLAS linear only rows{rows} C{C}", sec, flops=fl, bound="tensor")
     n = 4 * 128 * 128
     eu = rn(n); er = [rn(n) for _ in range(5)]; m = torch.rand(5, n, device="cuda"); lat = rn(n)
     sec = timeit(lambda: ops.region_blend_cfg(eu, er, m, 8.5, latents=lat, dt_sigma=-0.3))

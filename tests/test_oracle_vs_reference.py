@@ -65,3 +65,59 @@ def test_attention_fontsize_and_injection(ref):
         o = uo.attention(sd, "a", 2, hs, ctx, c)
     assert torch.allclose(o, o_ref, atol=1e-6) and torch.allclose(c.out[0], pavg_ref, atol=1e-7)
     assert torch.allclose(c.out[1], p_ref, atol=1e-7)
+
+
+# --------------------------------------------------------------------------- host-side text preparation
+class _Tok:
+    def _tokenize(self, text):
+        return text.lower().replace(",", " ,").split()
+
+
+class _Model:
+    tokenizer = _Tok()
+
+
+_DELTAS = [
+    {"ops": [{"insert": "a church "}, {"attributes": {"color": "#fd6c9e"}, "insert": "garden"},
+             {"insert": " with "}, {"attributes": {"font": "slabo"}, "insert": "mountains"},
+             {"attributes": {"size": "60px"}, "insert": " snowy"}, {"attributes": {"link": "a red sun"}, "insert": " sky"},
+             {"insert": "\n"}]},
+    {"ops": [{"attributes": {"font": "mirza"}, "insert": "a lake"}, {"attributes": {"font": "mirza"}, "insert": " at dawn"},
+             {"insert": ", "}, {"attributes": {"color": "#00ff00", "size": "18px", "strike": True}, "insert": "reeds"},
+             {"insert": " and a "}, {"attributes": {"color": "#a52a2a"}, "insert": "boat"}, {"insert": "\n"}]},
+    {"ops": [{"insert": "a plain prompt without attributes\n"}]},
+]
+
+
+@pytest.mark.parametrize("delta", _DELTAS)
+def test_richtext_utils_match_the_reference_functions(ref, delta):
+    """rtti_b200.richtext_utils against utils/richtext_utils.py of the unmodified reference on the same Quill deltas:
+    parse_json :74-136, get_region_diffusion_input :139-185, get_attention_control_input :188-209,
+    get_gradient_guidance_input :212-234 — identical prompts, token ids, font sizes and target colours."""
+    from rtti_b200 import richtext_utils as ru
+    rr = ref.richtext_utils
+
+    def same(a, b):
+        if torch.is_tensor(a) or torch.is_tensor(b):
+            return torch.is_tensor(a) and torch.is_tensor(b) and a.shape == b.shape and torch.allclose(a.float().cpu(), b.float().cpu())
+        if isinstance(a, (list, tuple)):
+            return isinstance(b, (list, tuple)) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        return a == b
+
+    out_r = rr.parse_json(delta)
+    out_p = ru.parse_json(delta, device="cpu")
+    assert len(out_r) == len(out_p) == 9
+    for i, (a, b) in enumerate(zip(out_r, out_p)):
+        assert same(a, b), f"parse_json output {i}: {a!r} vs {b!r}"
+    base, styles, notes, note_t, cspans, cnames, crgbs, sizes, use_grad = out_r
+    pr, idr, btr = rr.get_region_diffusion_input(_Model(), base, styles, notes, note_t, cspans, cnames)
+    pp, idp, btp = ru.get_region_diffusion_input(_Model(), base, styles, notes, note_t, cspans, cnames)
+    assert pr == pp and btr == btp and same(idr, idp)
+    tr = rr.get_attention_control_input(_Model(), btr, sizes)
+    tp = ru.get_attention_control_input(_Model(), btp, sizes, device="cpu")
+    assert set(tr) == set(tp) and all(same(tr[k], tp[k]) for k in tr)
+    tr2, cr = rr.get_gradient_guidance_input(_Model(), btr, cspans, crgbs, dict(tr), color_guidance_weight=0.5)
+    tp2, cp = ru.get_gradient_guidance_input(_Model(), btp, cspans, out_p[6], dict(tp), color_guidance_weight=0.5)
+    assert same(cr, cp) and set(tr2) == set(tp2)
+    for k in tr2:
+        assert same(tr2[k], tp2[k]), k

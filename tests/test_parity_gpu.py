@@ -388,3 +388,231 @@ def test_full_size_sd15_and_sdxl_runs_properties():
                      prompt_embeds=ctx[1:], negative_prompt_embeds=ctx[:1], pooled_prompt_embeds=te[1:],
                      negative_pooled_prompt_embeds=te[:1], output_type="latent", run_rich_text=True, inject_selfattn=0.5).images
     assert torch.equal(out2, out3)
+
+
+# ----------------------------------------------------------------------------- full-size parity against the CPU oracle
+def _err_stats(got, ref):
+    err = (got.float() - ref.float()).abs()
+    tol = 2e-2 + 2e-2 * ref.float().abs()
+    q = torch.quantile(err.flatten()[:: max(1, err.numel() // 200000)], torch.tensor([0.5, 0.99]))
+    return dict(max=float(err.max()), mean=float(err.mean()), p50=float(q[0]), p99=float(q[1]), ref_absmax=float(ref.abs().max()),
+                frac_out=float((err > tol).float().mean()))
+
+
+def _full_size_step(kind):
+    """One rich-text denoising step at BASELINE.json's full size (random weights of the real architecture), every
+    batched pass and the blended result against the fp32 CPU oracle running the reference's sequential pass order
+    (models/region_diffusion_sdxl.py:779-846 / models/region_diffusion.py:99-148): uncond, base + font sizes, reference
+    uncond / base (its self-attention probabilities and the up_blocks.1.resnets.1 feature stored), 2 region passes
+    with both injected, masked blend + CFG + scheduler step.  Tolerance per element: 2e-2 + 2e-2 |ref| (fp16 storage
+    against fp32); mean / median / 99th-percentile errors are printed."""
+    from oracle import sampler_oracle as sam, schedulers_oracle as so, unet_oracle as uo
+    xl = kind == "sdxl"
+    cfg = uo.sdxl_config() if xl else uo.sd15_config()
+    sd = uo.make_state_dict(cfg, 11)
+    S = 128 if xl else 64
+    pooled = _pooled(cfg) if xl else 0
+    N = 3
+    inp = synth.synth_inputs(cfg.cross_attention_dim, pooled, N, S, 61)
+    tfd = synth.font_sizes()
+    # ---- oracle, recording every pass
+    rec = []
+    base_fn = sam.make_unet_fn(sd, cfg)
+
+    def rec_fn(sample, t, ctx, added, ctrl):
+        y = base_fn(sample, t, ctx, added, ctrl)
+        rec.append(y.clone())
+        return y
+
+    sch = so.EulerDiscreteSchedulerOracle() if xl else so.PNDMSchedulerOracle()
+    sch.set_timesteps(4)
+    lat0 = inp["latents"] * (sch.init_noise_sigma if xl else 1.0)
+    trace = []
+    added = {"text_embeds": inp["text_embeds"], "time_ids": inp["time_ids"]} if xl else None
+    import bench
+    torch.set_num_threads(bench.host_threads())   # affinity mask capped by the cgroup CPU quota (oversubscription is ruinous)
+    ref_lat = sam.rich_text_loop(rec_fn, _OneStep(sch), inp["ctx"], inp["masks"], lat0.clone(), 4, 8.5, xl=xl, added_cond=added,
+                                 text_format_dict=tfd, inject_selfattn=0.5, inject_background=0.5, trace=trace)
+    assert len(rec) == 2 + 2 + (N - 1)
+    # ---- product: the same step as ONE batched call
+    from rtti_b200.unet import UNet2DConditionModel, UNetConfig
+    with torch.device("cuda"):   # parameters are created on the GPU: the CPU default init of 2.6 B parameters takes minutes
+        unet = UNet2DConditionModel(UNetConfig.from_dict(cfg.__dict__))
+    unet.load_state_dict(sd)
+    unet.finalize("cuda")
+    del sd
+    got = {}
+    if xl:
+        from rtti_b200.region_diffusion_sdxl import RegionDiffusionXL
+        model = RegionDiffusionXL(device="cuda", unet=unet, vae=None)
+        model.use_cuda_graphs = False
+        model.masks = [m.cuda() for m in inp["masks"]]
+        model.scheduler.set_timesteps(4)
+        orig = model._unet_pass
+
+        def spy(st, x, t, local, fis):
+            got["eps"] = orig(st, x, t, local, fis).clone()
+            got["local"] = list(local)
+            return got["eps"]
+
+        model._unet_pass = spy
+        lat = inp["latents"].cuda().half() * model.scheduler.init_noise_sigma
+        st = model.prepare_rich_text(inp["ctx"].cuda().half(), inp["text_embeds"].cuda().half(), inp["time_ids"].cuda(), lat,
+                                     model.scheduler.timesteps[:1], 8.5, False, 0.5, 0.5, {k: v for k, v in tfd.items()})   # one-step run, as the oracle's
+        with torch.no_grad():
+            model.rich_text_step(st, 0)
+        out_lat, noise_pred, passes = st.latents, st.noise_pred, st.passes
+    else:
+        from rtti_b200.region_diffusion import RegionDiffusion
+        model = RegionDiffusion(device="cuda", unet=unet, vae=None)
+        model.masks = [m.cuda() for m in inp["masks"]]
+        orig_unet = model.unet.forward
+
+        def spy_unet(*a, **k):
+            out = orig_unet(*a, **k)
+            got.setdefault("eps", out["sample"].clone())
+            return out
+
+        model.unet.forward = spy_unet
+        model.scheduler = _OneStep(model.scheduler)
+        out_lat = model.produce_latents(inp["ctx"].cuda(), num_inference_steps=4, guidance_scale=8.5, latents=inp["latents"].clone(),
+                                        text_format_dict=tfd, inject_selfattn=0.5, inject_background=0.5)
+        noise_pred = None
+        passes = [dict(kind=k) for k in "ABCD"] + [dict(kind="E")] * (N - 1)
+    torch.cuda.synchronize()
+    # oracle call order: A, B, C, D, E_1.. == product batch order
+    report = {}
+    for i, p in enumerate(passes):
+        report[f"pass {p['kind']}{p.get('region', '')}"] = _err_stats(got["eps"][i:i + 1].cpu(), rec[i])
+    if noise_pred is not None:
+        report["blended noise_pred"] = _err_stats(noise_pred.cpu(), trace[0]["noise_pred"])
+    report["latents after the step"] = _err_stats(out_lat.cpu(), ref_lat)
+    for k, v in report.items():
+        print(f"[full-size {kind}] {k}: " + " ".join(f"{a}={b:.4g}" for a, b in v.items()))
+    bad = {k: v for k, v in report.items() if v["frac_out"] > 0 and not k.startswith("latents")}
+    assert not bad, f"outside 2e-2 + 2e-2|ref|: {bad}"
+    lat_err = report["latents after the step"]
+    assert lat_err["max"] <= 5e-3 * lat_err["ref_absmax"] + 3e-2 * lat_err["ref_absmax"], lat_err
+
+
+class _OneStep:
+    """Scheduler wrapper that ends the sampling loop after its first step (full-size oracle passes cost ~15 s each)."""
+
+    def __init__(self, inner):
+        self.__dict__["inner"] = inner
+
+    def __getattr__(self, k):
+        return getattr(self.__dict__["inner"], k)
+
+    def set_timesteps(self, n, **kw):
+        self.inner.set_timesteps(n, **kw)
+        self.__dict__["timesteps"] = self.inner.timesteps[:1]
+
+
+def test_full_size_sd15_step_matches_oracle():
+    _full_size_step("sd15")
+
+
+def test_full_size_sdxl_step_matches_oracle():
+    _full_size_step("sdxl")
+
+
+# ----------------------------------------------------------------------------- the §8b plug-in
+def test_b200_region_attn_processor_contract(golden_dir):
+    """B200RegionAttnProcessor on a stand-in for the reference's `Attention` module (the attributes the processor
+    contract reads: heads, scale, to_q/k/v, to_out) against the golden outputs of the UNMODIFIED reference module
+    (tests/golden/attention.npz): plain call, font-size `attn_weights`, `real_attn_probs` injection through the lazy
+    handle the store hook keeps (models/region_diffusion_sdxl.py:1070-1082 -> :1023-1029), and `attention_probs_avg`.
+    Contract: models/attention_processor.py:1114-1123, 1183."""
+    import types
+    from rtti_b200.attention_processor import B200RegionAttnProcessor, LazyAttentionProbs
+    g = _load(golden_dir, "attention.npz")
+    heads = 4
+    for tag in ("cross", "self"):
+        W = {k[len(tag) + 3:]: torch.from_numpy(g[k]).cuda() for k in g.files if k.startswith(f"{tag}_w_")}
+        lin = lambda w, b=None: types.SimpleNamespace(weight=w, bias=b)
+        attn = types.SimpleNamespace(heads=heads, scale=(W["to_q.weight"].shape[0] // heads) ** -0.5,
+                                     to_q=lin(W["to_q.weight"]), to_k=lin(W["to_k.weight"]), to_v=lin(W["to_v.weight"]),
+                                     to_out=[lin(W["to_out.0.weight"], W["to_out.0.bias"])])
+        hs = torch.from_numpy(g[f"{tag}_hs"]).cuda()
+        enc = torch.from_numpy(g[f"{tag}_ctx"]).cuda() if tag == "cross" else None
+        proc = B200RegionAttnProcessor(return_probs_avg=True)
+        out, extra = proc(attn, hs, encoder_hidden_states=enc)
+        assert isinstance(extra, list) and len(extra) == 2 and out.dtype == hs.dtype and out.shape == hs.shape
+        pavg, probs = extra
+        assert isinstance(probs, LazyAttentionProbs) and probs.detach() is probs
+        nk = 77 if tag == "cross" else hs.shape[1]
+        assert tuple(probs.shape) == (hs.shape[0] * heads, hs.shape[1], nk)
+        _close(out.float().cpu(), g[f"{tag}_out"], 4e-3, 2e-2, f"processor {tag} output")
+        _close(pavg.float().cpu(), g[f"{tag}_pavg"], 1e-3, 0, f"processor {tag} probs_avg")
+        if tag == "cross":
+            aw = {"word_pos": torch.LongTensor([2, 5, 5, 9]), "font_size": torch.FloatTensor([2.0, 0.5, 3.0, -1.5])}
+            out, (pavg, _) = proc(attn, hs, None, aw, encoder_hidden_states=enc)   # positional, as the pre-hook passes them
+            _close(out.float().cpu(), g["cross_fs_out"], 4e-3, 2e-2, "processor font-size output")
+            _close(pavg.float().cpu(), g["cross_fs_pavg"], 1e-3, 0, "processor font-size probs_avg")
+        else:
+            hs2 = torch.from_numpy(g["self_inj_hs"]).cuda()
+            out, _ = B200RegionAttnProcessor()(attn, hs2, probs)                   # real_attn_probs, positional (:1028)
+            _close(out.float().cpu(), g["self_inj_out"], 4e-3, 2e-2, "processor injected output")
+            with pytest.raises(TypeError):
+                B200RegionAttnProcessor()(attn, hs2, torch.zeros(8, 64, 64, device="cuda"))
+
+
+def test_color_guidance_pairs_masks_with_targets_like_zip():
+    """sample.py hands over R colour maps + the background map but R target colours; the reference's zip() drops the
+    extra map (models/region_diffusion_sdxl.py:857). R + 1 masks with R targets must equal R masks with R targets."""
+    cfg, model = _xl_model(2)
+    S = 128
+    inp = synth.synth_inputs(cfg.cross_attention_dim, _pooled(cfg), 3, S, 31)
+    lat = (inp["latents"] * 3).cuda().half()
+    eps = inp["latents"].flip(-1).cuda().half()
+    tfd = synth.color_dict(inp["masks"], S, 1.0)
+    a = model._color_guidance(lat, eps, 500, tfd)
+    loss_a = float(model.last_step_stats["color_loss"])
+    tfd2 = dict(tfd)
+    bg = torch.nn.functional.interpolate(inp["masks"][1], (S * 8, S * 8), mode="bicubic", antialias=True).clamp(0, 1)
+    tfd2["color_obj_atten"] = tfd["color_obj_atten"] + [bg]
+    b = model._color_guidance(lat, eps, 500, tfd2)
+    assert torch.equal(a, b) and float(model.last_step_stats["color_loss"]) == loss_a
+    from rtti_b200 import _lib, ops
+    with pytest.raises(_lib.RttiError):
+        ops.color_loss_fwd_bwd(torch.zeros(3, 64, 64, device="cuda"), torch.zeros(2, 64, 64, device="cuda"), torch.zeros(1, 3, device="cuda"))
+
+
+def test_product_captured_maps_give_the_reference_segment_labels(golden_dir):
+    """Whole token-map path on the tiny XL config: plain CFG pass of the PRODUCT with on-device fp32 capture ->
+    get_token_maps.
+      (1) the 32x32 affinity the clustering consumes equals the one the REFERENCE builds from the maps of its own plain
+          pass (tests/golden/xl_token_labels.npz, oracle/gen_golden.py xl_labels) to 1e-3;
+      (2) segment indices are BIT-EXACT against the pinned restatement of utils/attention_utils.py:233-341
+          (oracle/token_maps_oracle.py == the reference on identical maps, tests/golden/token_maps.npz) fed with the
+          product-captured maps, and the region masks agree to 1e-6;
+      (3) agreement with the reference's own label image is reported, not asserted: with random weights the affinity is
+          nearly uniform (the four clusters differ at the 1e-4 level), so which pixel falls in which k-means cell is
+          decided below the fp16-vs-fp32 difference of the two captures. Identical maps in -> identical labels is (2)."""
+    from oracle import token_maps_oracle as tmo
+    from rtti_b200.attention_utils import get_token_maps, self_affinity
+    g = _load(golden_dir, "xl_token_labels.npz")
+    cfg, model = _xl_model(2)
+    S = 128
+    inp = synth.synth_inputs(cfg.cross_attention_dim, _pooled(cfg), 3, S, 31)
+    ctx, te = inp["ctx"].cuda(), inp["text_embeds"].cuda()
+    model.register_tokenmap_hooks()
+    model.sample(height=S * 8, width=S * 8, num_inference_steps=12, guidance_scale=8.5, latents=inp["latents"].clone(),
+                 prompt_embeds=ctx[-1:], negative_prompt_embeds=ctx[:1], pooled_prompt_embeds=te[-1:],
+                 negative_pooled_prompt_embeds=te[:1], output_type="latent", run_rich_text=False)
+    _close(self_affinity(model.selfattn_maps).cpu().numpy()[::64], g["affinity_rows"], 1e-3, 0, "affinity rows")
+    obj = [torch.LongTensor([3]), torch.LongTensor([7, 8])]
+    masks, clusters, _ = get_token_maps(model.selfattn_maps, model.crossattn_maps, model.n_maps, None, S, S, obj, seed=6,
+                                        segment_threshold=0.3, num_segments=4, return_vis=True)
+    selfm = {k: v.cpu() for k, v in model.selfattn_maps.items()}
+    crossm = {k: v.cpu() for k, v in model.crossattn_maps.items()}
+    ref_masks, ref_clusters = tmo.get_token_maps(selfm, crossm, None, None, S, S, obj, seed=6, segment_threshold=0.3,
+                                                 num_segments=4, return_clusters=True)
+    assert np.array_equal(np.asarray(clusters), np.asarray(ref_clusters)), "segment indices differ from the pinned restatement"
+    _close(torch.cat(masks).cpu().numpy(), torch.cat(ref_masks).numpy(), 1e-6, 0, "region masks")
+    # informational: best-permutation agreement with the label image of the reference's own run
+    import itertools
+    got = np.asarray(clusters).reshape(-1)
+    best = max(float((np.array(p)[got] == g["labels"].reshape(-1)).mean()) for p in itertools.permutations(range(4)))
+    print(f"segment labels: {100 * best:.1f}% of the 1024 pixels agree with the reference's own run (best label permutation)")
