@@ -66,9 +66,26 @@ def cross_maps_mean(crossattn_maps, resolution=32):
     return torch.cat(outs).mean(0)
 
 
+_PALETTE = np.array([[68, 1, 84], [59, 82, 139], [33, 145, 140], [94, 201, 98], [253, 231, 37], [230, 85, 13], [158, 1, 66],
+                     [116, 196, 118], [107, 174, 214], [240, 240, 240], [82, 82, 82], [188, 128, 189]], dtype=np.uint8)
+
+
+def render_segments(clusters, scale=8):
+    """uint8 RGB image of the segment label map (the reference returns a matplotlib canvas of `plt.imshow(clusters)`,
+    utils/attention_utils.py:266-276; same content, not the same pixels: matplotlib is not a dependency here)."""
+    img = _PALETTE[np.asarray(clusters) % len(_PALETTE)]
+    return np.repeat(np.repeat(img, scale, axis=0), scale, axis=1)
+
+
+def render_token_maps(resized):
+    """uint8 grey image with the region masks side by side (stands in for plot_attention_maps, :96-149, 334-335)."""
+    tiles = [(m.clamp(0, 1) * 255).round().to(torch.uint8).cpu().numpy() for m in resized]
+    return np.concatenate(tiles, axis=1)
+
+
 def get_token_maps(selfattn_maps, crossattn_maps, n_maps, save_dir, width, height, obj_tokens, seed=0,
                    tokens_vis=None, preprocess=False, segment_threshold=0.3, num_segments=5, return_vis=False,
-                   save_attn=False, device=None):
+                   save_attn=False, device=None, return_clusters=False):
     """Same signature and return value as utils/attention_utils.py:233-341: a list of N masks
     [1, 4, height, width] fp32 (spans..., background) that sum to one per pixel."""
     from sklearn.cluster import SpectralClustering
@@ -107,6 +124,8 @@ def get_token_maps(selfattn_maps, crossattn_maps, n_maps, save_dir, width, heigh
     resized = _resize(maps[:, None], (height, width))[:, 0].clamp(0, 1)     # (height, width) order, :325
     resized = resized / (resized.sum(0, True) + 1e-8)
     out = [m[None, None].repeat(1, 4, 1, 1).to(torch.float32) for m in resized]
+    if return_clusters:   # (masks, int label image): extension used by the tests
+        return out, clusters
     if return_vis:
-        return out, clusters, None
+        return out, render_segments(clusters), render_token_maps(resized)
     return out

@@ -112,7 +112,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (use_fs && threadIdx.x == 0) {
     for (int i = 0; i < p.n_fs; ++i) {
       int pos = p.word_pos[i];
-      if (pos >= 0 && pos < KT) fs_w[pos] = p.font_size[i];
+      if (pos >= 0 && pos < p.n_k) fs_w[pos] = p.font_size[i];   // the reference would raise an index error beyond the 77 keys
     }
   }
   if (KT == 80) __syncthreads();
@@ -477,6 +477,9 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
   dim3 grid((n_q + 127) / 128, (heads + p.heads_per_cta - 1) / p.heads_per_cta, batch);
   cudaStream_t st = (cudaStream_t)stream;
 #define RTTI_LAUNCH(KT_, ND_, CAP_) return launch<KT_, ND_, CAP_>(tq, tk, tv, to, p, grid, st)
+  if (KT == 80 && ndch == 1 && !want_cap)   // persistent streaming kernel (attn_cross.cu); capture / head_dim > 64 stay here
+    return launch_attn_cross(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.fs_mask, word_pos, font_size,
+                             p.n_fs, st);
   if (KT == 80) {
     if (want_cap) {
       if (ndch == 1) RTTI_LAUNCH(80, 1, true);

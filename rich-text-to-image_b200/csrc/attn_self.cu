@@ -27,8 +27,14 @@
 //     read S_j only after it) and that P V_{j-1} has completed from `p_full` (they write P_j only after it), so it
 //     refills the K stage of tile j and the V stage of tile j-1 at those points;
 //   * lazy rescale of O (only when a row max grows by more than 2^8) on all NV accumulators.
+#include <stdlib.h>
+
 #include "ptx.cuh"
 #include "rtti_internal.h"
+
+#ifndef SA_POLY_DEFAULT
+#define SA_POLY_DEFAULT 4
+#endif
 
 namespace rtti {
 
@@ -45,30 +51,46 @@ namespace sa {
 constexpr int KT = 64;
 constexpr int Q_TILE = 128 * 128;   // bytes
 constexpr int KV_TILE = KT * 128;   // 8 KB
-constexpr int THREADS = 160;
 template <int NV> struct Cfg {
   static constexpr int KST = 3;                                // K / V ring depth
   static constexpr int PBUF = NV == 1 ? 1 : 2;                 // P buffers in TMEM
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + Q_TILE;
   static constexpr int OFF_V = OFF_K + KST * KV_TILE;
+  static constexpr int SPLIT = NV == 1 ? 1 : 2;                // softmax threads per query row
+  static constexpr int THREADS = 32 * (4 * SPLIT + 1);
   static constexpr int OFF_BAR = OFF_V + KST * NV * KV_TILE;
-  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;      // + alignment slack
+  static constexpr int OFF_RED = OFF_BAR + 128;                // groups: row-max / row-sum exchange, 3 x 2 x 128 floats
+  static constexpr int SMEM_BYTES = OFF_RED + (SPLIT == 2 ? 3 * 2 * 128 * 4 : 0) + 1024;   // + alignment slack
   static constexpr uint32_t COLS_A = NV == 1 ? 128 : 512;      // S, (P), O
   static constexpr uint32_t COL_P = 64;                        // groups: P buffers at [64, 128)
   static constexpr uint32_t COL_O = NV == 1 ? 64 : 128;
-  static constexpr int MAX_REGS = NV == 1 ? 136 : 255;         // 65536 / (160 threads x 3 CTAs), 8-register granules
+  static constexpr int MAX_REGS = NV == 1 ? 136 : 224;         // 65536 / (160 threads x 3 CTAs) resp. / 288 threads, 8-register granules
 };
+// 2^x for x <= ~8 on the FMA / ALU pipes, two lanes at a time with the packed fp32 instructions of sm_100: round-to-nearest
+// split x = n + f (magic-number add), cubic minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, below the
+// fp16 rounding of P), n added into the exponent field. Inputs below -126 (masked keys: -inf) clamp to 2^-126 -> 0 in fp16.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f); x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);   // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float2 t = add_f32x2(x, magic);
+  const float2 f = add_f32x2(x, make_float2(12582912.f - t.x, 12582912.f - t.y));
+  float2 pl = fma_f32x2(make_float2(0.0551716685f, 0.0551716685f), f, make_float2(0.2426111251f, 0.2426111251f));
+  pl = fma_f32x2(pl, f, make_float2(0.6932609677f, 0.6932609677f));
+  pl = fma_f32x2(pl, f, make_float2(0.9999280572f, 0.9999280572f));
+  return make_float2(__uint_as_float(__float_as_uint(pl.x) + (__float_as_uint(t.x) << 23)),
+                     __uint_as_float(__float_as_uint(pl.y) + (__float_as_uint(t.y) << 23)));
+}
 }  // namespace sa
 
-template <int NV>
-__global__ void __launch_bounds__(sa::THREADS) __maxnreg__((sa::Cfg<NV>::MAX_REGS))
+template <int NV, int POLY>
+__global__ void __launch_bounds__(sa::Cfg<NV>::THREADS) __maxnreg__((sa::Cfg<NV>::MAX_REGS))
 attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                  const __grid_constant__ AttnSelfParams p) {
   using namespace sa;
   using C = Cfg<NV>;
-  constexpr int KST = C::KST, PBUF = C::PBUF;
+  constexpr int KST = C::KST, PBUF = C::PBUF, CW = 4 * C::SPLIT;   // CW: index of the control warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -93,12 +115,12 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int nv = NV == 1 ? 1 : p.nv[grp];
   const int nt = p.n_k_tiles;
 
-  if (warp == 4) {
+  if (warp == CW) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
       mbar_init(q_full, 1);
       for (int i = 0; i < KST; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
-      mbar_init(s_full, 1); mbar_init(s_free, 128); mbar_init(&p_full[0], 128); mbar_init(&p_full[1], 128);
+      mbar_init(s_full, 1); mbar_init(s_free, 128 * C::SPLIT); mbar_init(&p_full[0], 128 * C::SPLIT); mbar_init(&p_full[1], 128 * C::SPLIT);
       mbar_init(&pv_done[0], 1); mbar_init(&pv_done[1], 1); mbar_init(o_full, 1);
       mbar_fence_init();
     }
@@ -114,7 +136,7 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const uint32_t tmem_p = NV == 1 ? tmem_slot[1] : tmem + C::COL_P;   // groups: buffer b at tmem_p + 32 b
   const uint32_t tmem_o = tmem + C::COL_O;
 
-  if (warp == 4) {
+  if (warp == CW) {
     // ------------------------------------------------------------- control warp: TMA loads + MMA issue.
     // All 32 lanes run the loop (uniform control flow, operands in uniform registers); `el` predicates the issue.
     const uint32_t el = elect_one() ? 1u : 0u;
@@ -184,61 +206,81 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       if (j == nt - 1) tc_commit_p(o_full, el);
     }
   } else {
-    // ------------------------------------------------------------- softmax + epilogue: thread == query row == TMEM lane
-    const int row = warp * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    const uint32_t tlane = tmem + lane_off;
+    // ------------------------------------------------------------- softmax + epilogue
+    // plain: thread == query row; groups: SPLIT = 2 threads per row (warps w and w + 4 share TMEM lane quadrant w & 3), each
+    // owning NCOL = 32 of the 64 key columns and 32 of the 64 output columns: a group CTA has an SM to itself, and one
+    // softmax warp per scheduler cannot hide its own TMEM / barrier / MUFU latencies (measured 1900 cycles per key tile
+    // against 768 tensor cycles); two per scheduler overlap each other. The row max is exchanged through shared memory.
+    constexpr int SPLIT = C::SPLIT, NCOL = KT / SPLIT;
+    const int quad = warp & 3, part = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tlane = tmem + lane_off + NCOL * part;
     const bool row_ok = (q0 + row) < p.n_q;
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+    float* red = reinterpret_cast<float*>(smem + C::OFF_RED);   // [2 tile parities][SPLIT][128] row maxima, then [SPLIT][128] row sums
     float m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < nt; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      float s[64];
-      tmem_ld32(tlane, reinterpret_cast<uint32_t*>(s));
-      tmem_ld32(tlane + 32, reinterpret_cast<uint32_t*>(s) + 32);
-      tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s));
-      tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s) + 32);
+      float s[NCOL];
+#pragma unroll
+      for (int c = 0; c < NCOL / 32; ++c) tmem_ld32(tlane + 32 * c, reinterpret_cast<uint32_t*>(s) + 32 * c);
+#pragma unroll
+      for (int c = 0; c < NCOL / 32; ++c) tmem_wait_ld_regs32(reinterpret_cast<uint32_t*>(s) + 32 * c);
       tc_fence_before();
       mbar_arrive(s_free);
-      const int valid = p.n_k - j * KT;
-      if (valid < KT) {
+      const int valid = p.n_k - j * KT - NCOL * part;
+      if (valid < NCOL) {
 #pragma unroll
-        for (int i = 0; i < KT; ++i)
+        for (int i = 0; i < NCOL; ++i)
           if (i >= valid) s[i] = -INFINITY;
       }
-      float mx = s[0];
+      float m4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-      for (int i = 1; i < KT; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 4; i < NCOL; i += 4) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) m4[c] = fmaxf(m4[c], s[i + c]);
+      }
+      float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      if (SPLIT == 2) {
+        float* rm = red + (j & 1) * 256;
+        rm[part * 128 + row] = mx;
+        asm volatile("bar.sync %0, 64;\n" ::"r"(1 + quad) : "memory");   // the two warps that share these 32 rows
+        mx = fmaxf(mx, rm[(part ^ 1) * 128 + row]);
+      }
       const float mxs = mx * p.scale_log2;
       if (j == 0) {
         m_ref = mxs;
       } else {
-        const bool need = mxs > m_ref + 8.f;   // lazy rescale: keeps P <= 2^8 in fp16
+        const bool need = mxs > m_ref + 8.f;   // lazy rescale: keeps P <= 2^8 in fp16 (identical in both threads of a row)
         if (__any_sync(0xffffffffu, need)) {
           mbar_wait(&pv_done[(j - 1) % PBUF], ((j - 1) / PBUF) & 1);   // O is being accumulated by P V_{j-1}
           tc_fence_after();
           const float alpha = need ? ex2_approx(m_ref - mxs) : 1.f;
           if (need) m_ref = mxs;
           l *= alpha;
-          for (int c = 0; c < 4 * nv; ++c) {
+          for (int c = 0; c < (4 / SPLIT) * nv; ++c) {   // this thread's NCOL output columns of every accumulator
+            const uint32_t oc = tmem_o + lane_off + 64u * (c / (4 / SPLIT)) + NCOL * part + 16 * (c % (4 / SPLIT));
             uint32_t o[16];
-            tmem_ld16(tmem_o + lane_off + 16 * c, o);
+            tmem_ld16(oc, o);
             tmem_wait_ld_regs16(o);
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tmem_o + lane_off + 16 * c, o);
+            tmem_st16(oc, o);
           }
         }
       }
-      const uint32_t tp = tmem_p + lane_off + 32u * (j % PBUF);
+      const uint32_t tp = tmem_p + lane_off + 32u * (j % PBUF) + (NCOL / 2) * part;
       const float2 nm2 = make_float2(-m_ref, -m_ref);
       float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-      uint32_t pk[32];
+      uint32_t pk[NCOL / 2];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < NCOL / 2; ++i) {
         const float2 x = fma_f32x2(make_float2(s[2 * i], s[2 * i + 1]), sc2, nm2);
-        const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+        // POLY > 0: every POLY-th pair is evaluated on the FMA pipe (sa::exp2_poly2) instead of the MUFU pipe
+        const float2 e = (POLY > 0 && i % (POLY > 0 ? POLY : 1) == POLY - 1) ? exp2_poly2(x)
+                                                                             : make_float2(ex2_approx(x.x), ex2_approx(x.y));
         if (i & 1) acc1 = add_f32x2(acc1, e); else acc0 = add_f32x2(acc0, e);
         pk[i] = pack_half2(e.x, e.y);
       }
@@ -246,13 +288,19 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_wait(&pv_done[j % PBUF], ((j / PBUF) - 1) & 1);   // when that MMA has long completed
         tc_fence_after();
       }
-      tmem_st32(tp, pk);
+      if (SPLIT == 1) tmem_st32(tp, pk); else tmem_st16(tp, pk);
       l += (acc0.x + acc0.y) + (acc1.x + acc1.y);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[j % PBUF]);
     }
     // ---- epilogue: O_v / l -> fp16 -> swizzled staging tile (the Q tile, dead by now) -> TMA store, one member at a time
+    if (SPLIT == 2) {   // row sum = the two column halves (the rescale factors applied to l were identical in both)
+      float* rl = red + 512;
+      rl[part * 128 + row] = l;
+      asm volatile("bar.sync %0, 64;\n" ::"r"(1 + quad) : "memory");
+      l += rl[(part ^ 1) * 128 + row];
+    }
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv_l = 1.f / l;
@@ -261,12 +309,13 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     for (int v = 0; v < nv; ++v) {
       if (v > 0) {
         if (threadIdx.x == 0) tma_store_wait_read();   // the previous member's store has drained the staging tile
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        asm volatile("bar.sync 5, %0;\n" ::"n"(128 * SPLIT) : "memory");
       }
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
+      for (int hh = 0; hh < 2 / SPLIT; ++hh) {
+        const int cb = SPLIT == 2 ? part : hh;          // which 32-column half of the 64 output columns
         uint32_t o[32];
-        tmem_ld32(tmem_o + lane_off + 64u * v + 32 * hh, o);
+        tmem_ld32(tmem_o + lane_off + 64u * v + 32 * cb, o);
         tmem_wait_ld_regs32(o);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -275,40 +324,54 @@ attn_self_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           w.y = pack_half2(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l);
           w.z = pack_half2(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l);
           w.w = pack_half2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + (((hh * 4 + q) ^ sw) << 4)) = w;
+          *reinterpret_cast<uint4*>(orow + (((cb * 4 + q) ^ sw) << 4)) = w;
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      asm volatile("bar.sync 5, %0;\n" ::"n"(128 * SPLIT) : "memory");
       const int b = p.vent[grp][v];
       if (threadIdx.x == 0) {
         tma_store_4d(&tm_o, smem + C::OFF_Q, 0, h, q0, b);
         tma_store_commit();
       }
-      if (p.lse != nullptr && row_ok)
+      if (p.lse != nullptr && row_ok && part == 0)
         p.lse[(static_cast<size_t>(b) * p.heads + h) * p.n_q + q0 + row] = m_ref + log2f(l);
     }
     if (threadIdx.x == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == CW) {
     tmem_dealloc<C::COLS_A>(tmem);
     if (NV == 1) tmem_dealloc<32>(tmem_p);
   }
 }
 
+// RTTI_ATTN_POLY = 0 | 2 | 3 | 4 (read once; default 4): fraction 1/POLY of the exponentials of the PLAIN kernel is evaluated by
+// a polynomial on the FMA pipe instead of MUFU.EX2 (the plain kernel is bound by the 16-lane/SM MUFU pipe). Measured on B200
+// (profiles/r02_kernels_selfattn_poly_sweep.jsonl): 1/4 -> +4.4 % / +4.8 % at the 64^2 / 32^2 level, 1/2 -> -1 % (issue-bound).
+static const int g_poly = [] { const char* e = getenv("RTTI_ATTN_POLY"); const int v = e ? atoi(e) : SA_POLY_DEFAULT; return (v == 2 || v == 3 || v == 4) ? v : 0; }();
+
+template <int NV, int POLY>
+static int launch_variant(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                          const AttnSelfParams& p, int n_groups, cudaStream_t stream) {
+  using C = sa::Cfg<NV>;
+  static const bool configured =
+      cudaFuncSetAttribute(attn_self_kernel<NV, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess;
+  if (!configured) return RTTI_ERR_CUDA;
+  dim3 grid((p.n_q + 127) / 128, p.heads, n_groups);
+  attn_self_kernel<NV, POLY><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
+}
+
 template <int NV>
 static int launch_class(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                         const AttnSelfParams& p, int n_groups, cudaStream_t stream) {
-  using C = sa::Cfg<NV>;
-  static const bool configured =
-      cudaFuncSetAttribute(attn_self_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess;
-  if (!configured) return RTTI_ERR_CUDA;
-  dim3 grid((p.n_q + 127) / 128, p.heads, n_groups);
-  attn_self_kernel<NV><<<grid, sa::THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
-  return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
+  if (NV == 1 && g_poly == 2) return launch_variant<NV, (NV == 1 ? 2 : 0)>(tq, tk, tv, to, p, n_groups, stream);
+  if (NV == 1 && g_poly == 3) return launch_variant<NV, (NV == 1 ? 3 : 0)>(tq, tk, tv, to, p, n_groups, stream);
+  if (NV == 1 && g_poly == 4) return launch_variant<NV, (NV == 1 ? 4 : 0)>(tq, tk, tv, to, p, n_groups, stream);
+  return launch_variant<NV, 0>(tq, tk, tv, to, p, n_groups, stream);
 }
 
 // Library-owned side stream + fork/join events, one set per device (created on first use, never destroyed).

@@ -23,6 +23,11 @@ int launch_attn_self(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
                      int batch, int heads, int head_dim, int n_q, int n_k, float scale_log2, const int8_t* qk_src,
                      float* lse, int max_group, cudaStream_t stream);
 
+// attn_cross.cu: 77-key cross-attention for head_dim <= 64 without capture (Q/O maps: 128-row boxes, K/V maps: 80-row boxes)
+int launch_attn_cross(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                      int batch, int heads, int head_dim, int n_q, int n_k, float scale_log2, unsigned long long fs_mask,
+                      const int* word_pos, const float* font_size, int n_fs, cudaStream_t stream);
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace rtti

@@ -89,9 +89,10 @@ class ClipTextEncoders:
         return torch.cat([unc, cond])
 
     @torch.no_grad()
-    def encode(self, prompt, negative_prompt, device):
+    def encode(self, prompt, negative_prompt, device, force_zeros_for_empty_prompt=True):
         """SDXL: penultimate hidden states of both encoders concatenated + pooled output of encoder 2
-        (region_diffusion_sdxl.py:326-440). negative_prompt=[''] is encoded, not zeroed (:368-373)."""
+        (region_diffusion_sdxl.py:326-440). negative_prompt=[''] is encoded, not zeroed; negative_prompt=None with
+        `force_zeros_for_empty_prompt` gives zero negative / negative-pooled embeddings (:368-373)."""
         def run(prompts):
             embs, pooled = [], None
             for tok, enc in ((self.tokenizer, self.text_encoder), (self.tokenizer_2, self.text_encoder_2)):
@@ -100,8 +101,11 @@ class ClipTextEncoders:
                 embs.append(out.hidden_states[-2])
             return torch.cat(embs, dim=-1), pooled
         prompt = [prompt] if isinstance(prompt, str) else list(prompt)
+        zero_negative = negative_prompt is None and force_zeros_for_empty_prompt
         negative_prompt = [negative_prompt or ""] if not isinstance(negative_prompt, (list, tuple)) else list(negative_prompt)
         pe, pp = run(prompt)
+        if zero_negative:
+            return pe, torch.zeros_like(pe[:1]), pp, torch.zeros_like(pp[:1])
         ne, npool = run(negative_prompt[:1])
         return pe, ne, pp, npool
 

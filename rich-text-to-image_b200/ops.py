@@ -83,6 +83,8 @@ def attention(q, k, v, heads, scale=None, qk_src=None, word_pos=None, font_size=
     if word_pos is not None and font_size is not None and fs_batch_mask:
         _req(word_pos, torch.int32, "word_pos"); _req(font_size, torch.float32, "font_size")
         n_fs = int(word_pos.numel())
+        if font_size.numel() != n_fs:
+            raise _lib.RttiError("attention: word_pos and font_size must have the same length")
     prof = PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -101,7 +101,7 @@ class RegionDiffusionXL:
     def encode_prompt(self, prompt, negative_prompt):
         if self.text_encoders is None:
             raise RuntimeError("no text encoders loaded: pass prompt_embeds / pooled_prompt_embeds explicitly")
-        return self.text_encoders.encode(prompt, negative_prompt, self.device)
+        return self.text_encoders.encode(prompt, negative_prompt, self.device, self.force_zeros_for_empty_prompt)
 
     def prepare_latents(self, height, width, generator=None, latents=None):
         shape = (1, self.unet.config.in_channels, height // self.vae_scale_factor, width // self.vae_scale_factor)
@@ -263,6 +263,8 @@ class RegionDiffusionXL:
         st.plan = region_parallel.RegionParallelPlan(st.passes, inject, group=self.region_group)
         word_pos, font_size = tfd.get("word_pos"), tfd.get("font_size")
         if word_pos is not None and font_size is not None:
+            if int(word_pos.max()) >= ctx.shape[1] or int(word_pos.min()) < 0:   # the reference's advanced indexing raises here
+                raise IndexError(f"word_pos {word_pos.tolist()} outside the {ctx.shape[1]} text tokens")
             st.word_pos = word_pos.to(dev, torch.int32).contiguous()
             st.font_size = font_size.to(dev, torch.float32).contiguous()
         else:

@@ -231,6 +231,7 @@ CASES = {
     "self_group5_d40": lambda: attn_case(6, 8, 40, 256, 256, qk_src=[0, 1, 1, 1, 1, 1]),
     "self_group5_xl32": lambda: attn_case(8, 20, 64, 1024, 1024, qk_src=[0, 1, 2, 3, 3, 3, 3, 3], fused_qkv=True),
     "self_rescale": lambda: rescale_case(),
+    "sanitizer_small": lambda: case_sanitizer_small(),
     # grouping disabled (RTTI_ATTN_MAX_GROUP=1): every entry evaluates its own softmax from its source's Q, K
     "g1:self_group5": lambda: attn_case(8, 2, 64, 512, 512, qk_src=[0, 1, 2, 3, 3, 3, 3, 3], fused_qkv=True),
 }
@@ -253,6 +254,37 @@ def rescale_case():
         torch.cuda.synchronize()
         o_ref, _, _ = ref_attention(q, k, v, H, scale=1.0, qk_src=src)
         ok &= report(f"rescale src={src}", o, o_ref, 2e-3, 2e-2)
+    return ok
+
+
+def case_sanitizer_small():
+    """Small shapes of every kernel family for compute-sanitizer (memcheck / racecheck run 10-100x slower)."""
+    import torch
+    from rtti_b200 import ops
+    ok = True
+    ok &= attn_case(2, 2, 64, 256, 256)                                  # plain self-attention (3 CTAs/SM kernel)
+    ok &= attn_case(4, 2, 64, 192, 192, qk_src=[0, 1, 1, 1])             # grouped self-attention (2 threads per row)
+    ok &= attn_case(2, 2, 64, 128, 77, fs=True, cap=True)                # cross-attention, font sizes + capture
+    ok &= attn_case(1, 2, 80, 128, 128, want_lse=True)                   # head_dim 80 (128-key-tile kernel) + probs mean
+    x = (torch.randn(2, 256, 64, device="cuda") * 2).half(); ga = torch.randn(64, device="cuda").half(); be = torch.randn(64, device="cuda").half()
+    ops.groupnorm_silu(x, ga, be, 8, 1e-5, True)
+    ops.layernorm(x, ga, be, 1e-5)
+    ops.add_bias_layernorm(x.clone(), x.clone(), ga, ga, be, 1e-5)
+    ops.geglu(torch.randn(64, 128, device="cuda").half())
+    w = torch.randn(8 * 64, 64, device="cuda").half() / 8
+    ops.ff_geglu(x, w, torch.randn(8 * 64, device="cuda").half())
+    n = 4 * 32 * 32
+    eu = torch.randn(n, device="cuda").half(); m = torch.rand(2, n, device="cuda"); lat = torch.randn(n, device="cuda").half()
+    ops.region_blend_cfg(eu, [eu, lat], m, 8.5, latents=lat, dt_sigma=-0.3)
+    dec = torch.randn(3, 64, 64, device="cuda"); masks = torch.rand(1, 64, 64, device="cuda")
+    ops.color_loss_fwd_bwd(dec, masks, torch.tensor([[0.9, 0.4, 0.6]], device="cuda"))
+    ops.latent_guidance_update(lat, torch.randn(n, device="cuda"), torch.rand(n, device="cuda"), 0.5)
+    ops.bg_inject_blend(lat, eu, torch.rand(n, device="cuda"))
+    ops.predict_x0(lat, eu, 0.3)
+    x32 = torch.randn(1, 256, 64, device="cuda")
+    y, st = ops.gn32_silu_fwd(x32, torch.randn(64, device="cuda"), torch.randn(64, device="cuda"), 8, 1e-6, True)
+    ops.gn32_silu_bwd(x32, torch.randn_like(x32), torch.randn(64, device="cuda"), torch.randn(64, device="cuda"), st, 8, True)
+    torch.cuda.synchronize()
     return ok
 
 

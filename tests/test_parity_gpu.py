@@ -489,10 +489,14 @@ def _full_size_step(kind):
     report["latents after the step"] = _err_stats(out_lat.cpu(), ref_lat)
     for k, v in report.items():
         print(f"[full-size {kind}] {k}: " + " ".join(f"{a}={b:.4g}" for a, b in v.items()))
-    bad = {k: v for k, v in report.items() if v["frac_out"] > 0 and not k.startswith("latents")}
-    assert not bad, f"outside 2e-2 + 2e-2|ref|: {bad}"
-    lat_err = report["latents after the step"]
-    assert lat_err["max"] <= 5e-3 * lat_err["ref_absmax"] + 3e-2 * lat_err["ref_absmax"], lat_err
+    bad = {k: v for k, v in report.items() if v["frac_out"] > 0 and k.startswith("pass ")}
+    assert not bad, f"UNet passes outside 2e-2 + 2e-2|ref|: {bad}"
+    # blended quantities: eps = eps_u + g (eps_t - eps_u) with g = 8.5 amplifies the per-pass error by up to 2g - 1 = 16, so
+    # they are held to the latent-trajectory tolerance of this file: 0.5 % of the dynamic range + 3 % per element
+    for k in ("blended noise_pred", "latents after the step"):
+        if k in report:
+            e = report[k]
+            assert e["max"] <= 5e-3 * e["ref_absmax"] + 3e-2 * e["ref_absmax"] and e["mean"] <= 2e-3 * e["ref_absmax"], (k, e)
 
 
 class _OneStep:
@@ -603,8 +607,8 @@ def test_product_captured_maps_give_the_reference_segment_labels(golden_dir):
                  negative_pooled_prompt_embeds=te[:1], output_type="latent", run_rich_text=False)
     _close(self_affinity(model.selfattn_maps).cpu().numpy()[::64], g["affinity_rows"], 1e-3, 0, "affinity rows")
     obj = [torch.LongTensor([3]), torch.LongTensor([7, 8])]
-    masks, clusters, _ = get_token_maps(model.selfattn_maps, model.crossattn_maps, model.n_maps, None, S, S, obj, seed=6,
-                                        segment_threshold=0.3, num_segments=4, return_vis=True)
+    masks, clusters = get_token_maps(model.selfattn_maps, model.crossattn_maps, model.n_maps, None, S, S, obj, seed=6,
+                                     segment_threshold=0.3, num_segments=4, return_clusters=True)
     selfm = {k: v.cpu() for k, v in model.selfattn_maps.items()}
     crossm = {k: v.cpu() for k, v in model.crossattn_maps.items()}
     ref_masks, ref_clusters = tmo.get_token_maps(selfm, crossm, None, None, S, S, obj, seed=6, segment_threshold=0.3,
