@@ -345,11 +345,36 @@ def run_product_xl(args, rank, world, local_rank):
     warm_idx = sorted({0, min(n_t - 1, int(cfg["inject_background"] * n_t)), n_t - 1})
     w_idx = spread(args.warmup, n_t)
     t_idx = spread(args.steps, n_t)
+    def peer_errors():
+        """True on every rank if any rank's peer-memory waits (RemoteQK, exchange, stripe arena) timed out."""
+        bad = any(rq is not None and rq.error() for rq in model._remote.values())
+        for obj in list(model._exchanges.values()) + [e.arena for e in model._stripe_engines.values()]:
+            try:
+                obj.check()
+            except RuntimeError:
+                bad = True
+        t = torch.tensor([1.0 if bad else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(t.item() > 0)
+
+    fallback = None
     with torch.no_grad():
         for i in warm_idx + w_idx:
             for st in states:
                 model.rich_text_step(st, i)
         barrier()
+        if world > 1 and peer_errors():
+            # safety net: a peer wait timed out during warm-up (never seen; the kernels give up after seconds instead of
+            # hanging). Fall back to the round-1 scheme — pass D replicated, eager guidance — and say so in the line.
+            fallback = "peer wait timed out in warm-up: remote_qk and graph_guidance disabled for this run"
+            print("bench.py: " + fallback, file=sys.stderr, flush=True)
+            model.remote_qk = model.graph_guidance = False
+            states = [fresh_state(w) for w in workloads]
+            for i in warm_idx + w_idx:
+                for st in states:
+                    model.rich_text_step(st, i)
+            barrier()
         # ------------------------------------------------------------- device-resident timing
         clocks = ClockSampler(local_rank) if rank == 0 else None
         launches0 = ops.LAUNCHES
@@ -402,27 +427,46 @@ def run_product_xl(args, rank, world, local_rank):
         if "color_obj_atten" in p["tfd"]:
             ts += [*p["tfd"]["color_obj_atten"], p["tfd"]["color_obj_atten_all"]]
         h2d += sum(x.numel() * x.element_size() for x in ts)
-    host_lat = torch.empty(1, 4, 128, 128, dtype=torch.float16).pin_memory()
+    # Results are read back through pinned double buffers, ONE STEP DEEP: step k's latents / loss are copied to the host
+    # asynchronously right after its launches and consumed (event wait + host read) after step k+1 has been issued, so the
+    # host work of a step (input staging, launches) overlaps the device work of the previous one. Every step still pays
+    # its own H2D of all inputs and its own D2H of the result inside the timed region.
+    host_lat = [torch.empty(1, 4, 128, 128, dtype=torch.float16).pin_memory() for _ in range(2)]
+    host_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss = None
+
+    def drain(pend):
+        ev, slot = pend
+        ev.synchronize()
+        assert bool(torch.isfinite(host_lat[slot][0, 0, 0, :8].float()).all())
+        return float(host_loss[slot][0]) if cfg["color"] else None
+
     with torch.no_grad():
         barrier()
         t0 = time.perf_counter()
+        pending, k = None, 0
         for i in t_idx:
             for st, p in zip(states, pinned):
                 s2 = fresh_state(p)                      # H2D of this step's inputs from pinned host memory
                 s2.kv_caches = st.kv_caches              # prompt K/V projections and the captured UNet graphs are
                 s2.graphs = st.graphs                    # per-prompt state, kept across steps
                 model.rich_text_step(s2, i)              # the public step call
-                host_lat.copy_(s2.latents, non_blocking=False)      # D2H of the step result
-                if cfg["color"]:
-                    loss = float(model.last_step_stats["color_loss"].item())
+                host_lat[k & 1].copy_(s2.latents, non_blocking=True)       # D2H of the step result (async, pinned)
+                if cfg["color"] and "color_loss" in model.last_step_stats:
+                    host_loss[k & 1].copy_(model.last_step_stats["color_loss"], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    loss = drain(pending)
+                pending, k = (ev, k & 1), k + 1
+        loss = drain(pending)
         barrier()
         e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
-    d2h = (host_lat.numel() * 2 + (4 if cfg["color"] else 0)) * len(states)
+    d2h = (host_lat[0].numel() * 2 + (4 if cfg["color"] else 0)) * len(states)
 
     # ------------------------------------------------------------- whole sampling loop, wall clock (graphs warm)
     with torch.no_grad():
@@ -433,7 +477,7 @@ def run_product_xl(args, rank, world, local_rank):
             s2.kv_caches, s2.graphs = st.kv_caches, st.graphs
             for i in range(n_t):
                 model.rich_text_step(s2, i)
-            host_lat.copy_(s2.latents, non_blocking=False)
+            host_lat[0].copy_(s2.latents, non_blocking=False)
         barrier()
         loop_s = time.perf_counter() - t0
     tl = torch.tensor([loop_s], device=dev)
@@ -500,20 +544,25 @@ def run_product_xl(args, rank, world, local_rank):
         "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": bench_config(args.config),
         "execution": "the passes of a rank run as one batched, CUDA-graph-replayed UNet call",
-        "parallelism": (f"UNet passes region-parallel x{world} (fused peer-memory exchange)"
-                        + (f", colour guidance stripe-parallel x{world}" if cfg["color"] else "")
+        "parallelism": (f"UNet passes region-parallel x{world} (fused peer-memory exchange; "
+                        + ("pass D on one rank, its Q|K and injected feature pushed to the region-pass ranks over NVLink)"
+                           if model.remote_qk and model.fused_exchange else "pass D replicated on the region-pass ranks)")
+                        + (f", colour guidance stripe-parallel x{world}" + (" replayed as one CUDA graph" if model.graph_guidance else "")
+                           if cfg["color"] else "")
                         + (f"; {cfg['images']} images data-parallel first" if cfg["images"] > 1 else "")
                         if world > 1 else "single GPU"),
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "last_color_loss": loss},
+                "last_color_loss": loss,
+                "how": "RegionDiffusionXL.rich_text_step per step; all step inputs staged from pinned host memory every step, "
+                       "latents + loss copied back every step (async D2H, consumed one step later)"},
         "consistency": {"device_ms_per_step": ms / args.steps, "e2e_ms_per_step": 1000.0 * e2e_s / args.steps,
                         "device_le_e2e": ms / args.steps <= 1.02 * 1000.0 * e2e_s / args.steps},
         "sampling_loop": {"steps": n_t, "wall_s": loop_s, "steps_per_s": n_t * 1.0 / loop_s,
                           "what": f"all {n_t} steps of one rich-text sampling run in schedule order through rich_text_step "
                                   "(inputs from pinned host memory once, latents read back once; CUDA graphs warm)"},
         "roofline": roof, "roofline_cross_attention": cross, "breakdown_ms": breakdown,
-        "ranks_bit_identical": ranks_identical, "single_gpu_check": check,
+        "ranks_bit_identical": ranks_identical, "single_gpu_check": check, "fallback": fallback,
     }
     if world == 1 and not args.no_cpu_baseline:
         pps = passes_per_step(cfg) * cfg["images"]

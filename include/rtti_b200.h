@@ -190,14 +190,21 @@ int rtti_gather_blend_step(const void* const* peer_slots, void* const* peer_flag
  * rtti_gn32_silu_fwd/bwd_striped: GroupNorm(+SiLU) over a tensor of hw_total rows of which x holds this rank's
  *   hw_local rows (batch 1, groups <= 32). The statistics are reduced through peer memory inside the call:
  *   peer_sums (host, [world]): device pointers to each rank's fp32 [2 (seq parity)][2*groups] slot;
- *   peer_flags (host, [world]): device pointers to each rank's uint32 {sequence, error} words (zero-initialised);
- *   seq: 1, 2, 3, ... the same on every rank for the same call. All ranks obtain bit-identical statistics.
+ *   peer_flags (host, [world]): device pointers to each rank's uint32[9] {sequence, error, -, ..., [8] sequence base}
+ *   words (zero-initialised);
+ *   seq: 1, 2, 3, ... the same on every rank for the same call; the kernels add the local rank's sequence base word
+ *   to it (0 unless rtti_peer_seq_advance was called). All ranks obtain bit-identical statistics.
  *   workspace: fp32 [rtti_gn32_workspace_elems(1, hw_local, c, groups)].
  * rtti_halo_exchange: pad_local is this rank's conv input [1 + rows + 1][row_elems] fp32 with the interior rows
  *   already written; pushes the first / last interior row into the bottom / top halo row of pad_up / pad_down
  *   (peer-mapped pointers to the neighbours' buffers of the same shape; NULL at the image border, where the own
  *   halo row is zeroed instead), then waits until both neighbours have pushed theirs.
- *   flags_*: uint32[4] per rank {from_up, from_down, error, arrival counter}, zero-initialised, peer-mapped.
+ *   flags_*: uint32[9] per rank {from_up, from_down, error, arrival counter, -, -, -, -, sequence base}, zero-initialised,
+ *   peer-mapped; the effective sequence number is seq + flags_local[8].
+ * rtti_peer_seq_advance: flags_a[8] += da; flags_b[8] += db (either pointer may be NULL), stream-ordered. A caller that
+ *   numbers the exchanges of one colour-guidance evaluation 1..n and advances the bases by n afterwards passes the same
+ *   arguments every evaluation, so the evaluation can be captured ONCE in a CUDA graph and replayed (the sequence numbers
+ *   the ranks compare stay monotonic because the base lives in device memory).
  */
 int rtti_gn32_silu_fwd_striped(const float* x, const float* chan_bias, const float* gamma, const float* beta, float* y,
                                float* mean_rstd, float* workspace, int hw_local, long long hw_total, int c, int groups,
@@ -209,6 +216,22 @@ int rtti_gn32_silu_bwd_striped(const float* x, const float* chan_bias, const flo
                                void* const* peer_flags, int world, int rank, unsigned int seq, void* stream);
 int rtti_halo_exchange(float* pad_local, float* pad_up, float* pad_down, int rows, long long row_elems,
                        void* flags_local, void* flags_up, void* flags_down, unsigned int seq, void* stream);
+int rtti_peer_seq_advance(void* flags_a, unsigned int da, void* flags_b, unsigned int db, void* stream);
+
+/* Producer -> consumers hand-off of one activation over peer memory (multi-GPU; new relative to the single-GPU
+ * reference). On feature-injection steps the region passes consume the self-attention Q, K of the reference pass D in
+ * every layer and one resnet feature map (models/region_diffusion_sdxl.py:1018-1061, models/resnet.py:639-641); with the
+ * passes sharded over ranks, the rank that runs D pushes them to the ranks that run region passes.
+ * rtti_peer_push: copy rows x row_bytes (row stride src_row_stride_bytes; 16-byte multiples) into dst[0..n_dst) (host
+ *   array of peer-mapped pointers, n_dst <= 15), then publish event number seq + flags_local[8] to dst_flags[d][0].
+ *   flags_local: uint32[9] {-, error, -, arrival counter, ..., [8] sequence base}, zero-initialised.
+ * rtti_peer_wait: stream-ordered wait until flags_local[0] >= seq + flags_local[8] (~4 s timeout -> flags_local[1] =
+ *   0xDEAD, after which waits return immediately). Events are numbered 1, 2, ... within one UNet pass and the base is
+ *   advanced with rtti_peer_seq_advance at its end, so both calls are CUDA-graph replayable.
+ */
+int rtti_peer_push(const void* src, long long src_row_stride_bytes, int rows, int row_bytes, void* const* dst,
+                   void* const* dst_flags, int n_dst, void* flags_local, unsigned int seq, void* stream);
+int rtti_peer_wait(void* flags_local, unsigned int seq, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,10 @@ SIGNATURES = {
                                            ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_int, c_int, ctypes.c_uint,
                                            c_void_p]),
     "rtti_halo_exchange": (c_int, [c_void_p] * 3 + [c_int, c_ll] + [c_void_p] * 3 + [ctypes.c_uint, c_void_p]),
+    "rtti_peer_seq_advance": (c_int, [c_void_p, ctypes.c_uint, c_void_p, ctypes.c_uint, c_void_p]),
+    "rtti_peer_push": (c_int, [c_void_p, c_ll, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_int,
+                               c_void_p, ctypes.c_uint, c_void_p]),
+    "rtti_peer_wait": (c_int, [c_void_p, ctypes.c_uint, c_void_p]),
 }
 
 _lib = None

@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "librtti_b200.so")
-SOURCES = ["common.cu", "elementwise.cu", "attn_fwd.cu", "attn_self.cu", "attn_cross.cu", "gemm_geglu.cu", "attn_probs_mean.cu", "gather_blend.cu", "vae_kernels.cu", "stripe_exchange.cu"]
+SOURCES = ["common.cu", "elementwise.cu", "attn_fwd.cu", "attn_self.cu", "attn_cross.cu", "gemm_geglu.cu", "attn_probs_mean.cu", "gather_blend.cu", "vae_kernels.cu", "stripe_exchange.cu", "peer_push.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",

@@ -45,7 +45,7 @@ constexpr int THREADS = 288;                // 2 softmax warpgroups + 1 control 
 constexpr int CW = 8;
 }  // namespace ca
 
-__global__ void __maxnreg__(224)   // 288 threads x 224 registers = one CTA per SM
+__global__ void __maxnreg__(168)   // 9 warps are checked as 12 (register allocation is verified per 4 sub-partitions): 65536 / (12 x 32) = 170
 attn_cross_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                   const __grid_constant__ AttnCrossParams p) {

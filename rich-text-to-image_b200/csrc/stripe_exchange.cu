@@ -14,6 +14,11 @@
 //     symmetric slot, publishes, waits for all peers and adds the slots in RANK ORDER, so every rank gets
 //     bit-identical statistics without a collective launch.
 //
+// Sequence numbers: `seq` is added to the SEQUENCE BASE word kept next to the local flags (flags[8], zero unless
+// rtti_peer_seq_advance has been called). A caller that numbers the exchanges of one colour-guidance call 1..n and
+// advances the base by n at the end of the call issues the same kernel arguments every call, so the whole call can be
+// captured once in a CUDA graph and replayed; the base lives in device memory and keeps the flags monotonic.
+//
 // Re-use safety without trailing barriers: pad buffers and sum slots are double-buffered by sequence parity. A
 // neighbour can push exchange s+2 only after its exchange s+1 completed, which needs this rank's push s+1, which
 // is stream-ordered after this rank's consumer of exchange s. A peer that never arrives trips a ~4 s timeout that
@@ -23,7 +28,11 @@
 
 namespace rtti {
 
-// flags (uint32, local symmetric memory): [0] from_up, [1] from_down, [2] error, [3] CTA arrival counter
+// flags (uint32, local symmetric memory): [0] from_up, [1] from_down, [2] error, [3] CTA arrival counter, [8] sequence base
+constexpr int SEQ_BASE_WORD = 8;
+__device__ __forceinline__ unsigned int ld_seq_base(const unsigned int* flags) {
+  return *reinterpret_cast<const volatile unsigned int*>(flags + SEQ_BASE_WORD);
+}
 __global__ void __launch_bounds__(256) halo_exchange_kernel(float* __restrict__ pad, float* __restrict__ up,
                                                             float* __restrict__ down, int rows, long long row_vec,
                                                             unsigned int* fl, unsigned int* fl_up,
@@ -45,6 +54,7 @@ __global__ void __launch_bounds__(256) halo_exchange_kernel(float* __restrict__ 
     const unsigned int arrived = atomicAdd(&fl[3], 1u);
     if (arrived == gridDim.x - 1) {   // last CTA: every push of this rank is visible system-wide
       fl[3] = 0u;
+      seq += ld_seq_base(fl);
       __threadfence_system();
       if (up) st_release_sys(fl_up + 1, seq);      // I am my upper neighbour's "down"
       if (down) st_release_sys(fl_down + 0, seq);  // and my lower neighbour's "up"
@@ -58,7 +68,21 @@ __global__ void __launch_bounds__(256) halo_exchange_kernel(float* __restrict__ 
 
 }  // namespace rtti
 
+namespace rtti {
+__global__ void peer_seq_advance_kernel(unsigned int* a, unsigned int da, unsigned int* b, unsigned int db) {
+  if (a) a[SEQ_BASE_WORD] += da;
+  if (b) b[SEQ_BASE_WORD] += db;
+}
+}  // namespace rtti
+
 using namespace rtti;
+
+extern "C" int rtti_peer_seq_advance(void* flags_a, unsigned int da, void* flags_b, unsigned int db, void* stream) {
+  if (!flags_a && !flags_b) return RTTI_ERR_ARG;
+  if (((uintptr_t)flags_a | (uintptr_t)flags_b) & 3) return RTTI_ERR_ALIGN;
+  peer_seq_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned int*)flags_a, da, (unsigned int*)flags_b, db);
+  return cudaGetLastError() == cudaSuccess ? RTTI_OK : RTTI_ERR_CUDA;
+}
 
 extern "C" int rtti_halo_exchange(float* pad_local, float* pad_up, float* pad_down, int rows, long long row_elems,
                                   void* flags_local, void* flags_up, void* flags_down, unsigned int seq, void* stream) {

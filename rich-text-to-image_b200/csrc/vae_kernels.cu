@@ -231,7 +231,7 @@ static int gn32_check(const void* a, const void* b_, const void* c_, const void*
 // ---- stripe-parallel variant (multi-GPU colour guidance, see stripe_exchange.cu) -----------------------------
 struct PeerSums {
   float* sums[PEER_MAX_WORLD];          // per rank: float [2 parities][2 * groups], peer-mapped
-  unsigned int* flags[PEER_MAX_WORLD];  // per rank: [0] sequence word, [1] error word
+  unsigned int* flags[PEER_MAX_WORLD];  // per rank: [0] sequence word, [1] error word, [8] sequence base (local rank only)
   int world, rank;
   unsigned int seq;
 };
@@ -244,7 +244,9 @@ __global__ void __launch_bounds__(1024) gn32_finalize_peer_kernel(const float* _
                                                                   const PeerSums pp, int groups, int chunks,
                                                                   float n_total, float eps) {
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int par = (int)(pp.seq & 1u);
+  // effective sequence number = argument + the sequence base word next to this rank's flags (stripe_exchange.cu)
+  const unsigned int seq = pp.seq + *reinterpret_cast<const volatile unsigned int*>(pp.flags[pp.rank] + 8);
+  const int par = (int)(seq & 1u);
   if (g < groups) {
     float s0 = 0.f, s1 = 0.f;
     for (int k = lane; k < chunks; k += 32) {
@@ -264,10 +266,10 @@ __global__ void __launch_bounds__(1024) gn32_finalize_peer_kernel(const float* _
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
-    st_release_sys(pp.flags[pp.rank], pp.seq);
+    st_release_sys(pp.flags[pp.rank], seq);
   }
   if (threadIdx.x < pp.world && threadIdx.x != pp.rank) {
-    if (!wait_seq(pp.flags[threadIdx.x], pp.seq)) pp.flags[pp.rank][1] = 0xDEADu;
+    if (!wait_seq(pp.flags[threadIdx.x], seq)) pp.flags[pp.rank][1] = 0xDEADu;
   }
   __syncthreads();
   if (g < groups && lane == 0) {

@@ -71,9 +71,13 @@ def attention(q, k, v, heads, scale=None, qk_src=None, word_pos=None, font_size=
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, _F16, n)
-    B, nq, C = q.shape
+    B, nq, C = v.shape[0], q.shape[1], q.shape[2]
     nk = k.shape[1]
     D = C // heads
+    if q.shape[0] != B or k.shape[0] != B:
+        # Q / K handed over from another pass (e.g. the reference pass on a peer rank): every entry must name its source
+        if qk_src is None or q.shape[0] != k.shape[0] or max(qk_src) >= q.shape[0] or len(qk_src) != B:
+            raise _lib.RttiError("attention: q/k with a different batch than v need qk_src[b] < q.shape[0] for every entry of v")
     if out is None:
         out = torch.empty((B, nq, C), dtype=_F16, device=q.device)
     if scale is None:
@@ -416,6 +420,34 @@ def halo_exchange(pad, pad_ptr_up, pad_ptr_down, flags_local, flags_up, flags_do
                                 pad.shape[1] * pad.shape[2], ctypes.c_void_p(flags_local),
                                 ctypes.c_void_p(flags_up or 0), ctypes.c_void_p(flags_down or 0), int(seq), _stream())
     _lib.check(rc, "rtti_halo_exchange")
+    _count(1)
+
+
+def peer_seq_advance(flags_a, da, flags_b=0, db=0):
+    """flags_a[8] += da; flags_b[8] += db: advance the device-side sequence bases of the stripe exchange at the end of
+    one colour-guidance evaluation (rtti_peer_seq_advance), which makes the evaluation CUDA-graph replayable."""
+    lib = _lib.load()
+    rc = lib.rtti_peer_seq_advance(ctypes.c_void_p(flags_a or 0), int(da), ctypes.c_void_p(flags_b or 0), int(db), _stream())
+    _lib.check(rc, "rtti_peer_seq_advance")
+    _count(1)
+
+
+def peer_push(src, dst_ptrs, dst_flag_ptrs, flags_local, seq):
+    """src [rows, width] fp16 view (unit column stride, any row stride): copy into every peer buffer of `dst_ptrs` and
+    publish event `seq` to their flag words (rtti_peer_push). dst_ptrs / dst_flag_ptrs: ctypes c_void_p arrays."""
+    lib = _lib.load()
+    _req(src, _F16, "src")
+    assert src.dim() == 2 and src.stride(1) == 1
+    rc = lib.rtti_peer_push(_ptr(src), src.stride(0) * 2, src.shape[0], src.shape[1] * 2, dst_ptrs, dst_flag_ptrs,
+                            len(dst_ptrs), ctypes.c_void_p(flags_local), int(seq), _stream())
+    _lib.check(rc, "rtti_peer_push")
+    _count(1)
+
+
+def peer_wait(flags_local, seq):
+    """Stream-ordered wait for event `seq` of the producer rank (rtti_peer_wait)."""
+    lib = _lib.load()
+    _lib.check(lib.rtti_peer_wait(ctypes.c_void_p(flags_local), int(seq), _stream()), "rtti_peer_wait")
     _count(1)
 
 

@@ -66,7 +66,11 @@ class RegionDiffusionXL:
         self.fused_exchange = True   # multi-GPU: fused peer-memory gather+blend kernel instead of NCCL all-gather
         self.stripe_guidance = True  # multi-GPU: colour guidance (VAE fwd+bwd) split by image rows over the ranks
         self._stripe_engines = {}
+        self.graph_guidance = True   # replay decode -> colour loss -> decoder backward as one CUDA graph (launch-bound on >1 GPU)
+        self._guidance_graphs = {}
         self.region_group = None     # torch.distributed group the passes of one image are sharded over (None = all ranks)
+        self.remote_qk = True        # multi-GPU: pass D on one rank, its Q|K / feature pushed to the region-pass ranks
+        self._remote = {}            # (instead of replicating D on every rank that owns a region pass)
         self.last_step_stats = {}
 
     @classmethod
@@ -132,8 +136,18 @@ class RegionDiffusionXL:
             self.last_step_stats["color_loss"] = loss
             return g[None]
 
-        grad_lat = vae_guidance.image_and_latent_grad(self.vae, x0.float() / sf, grad_image,
-                                                      engine=self._stripe_engine(x0)) / (sf * math.sqrt(alpha))
+        z = x0.float() / sf
+        engine = self._stripe_engine(x0)
+        if self.graph_guidance and isinstance(self.vae, AutoencoderKLDecoder):
+            eng = engine if engine is not None else vae_guidance.default_engine(self.vae)
+            gkey = (id(eng), tuple(z.shape), tuple(masks.shape))
+            gg = self._guidance_graphs.get(gkey)
+            if gg is None:
+                gg = self._guidance_graphs[gkey] = vae_guidance.GuidanceGraph(eng)
+            self.last_step_stats["color_loss"], grad_lat = gg(z.contiguous(), masks, tgt)
+            grad_lat = grad_lat / (sf * math.sqrt(alpha))
+        else:
+            grad_lat = vae_guidance.image_and_latent_grad(self.vae, z, grad_image, engine=engine) / (sf * math.sqrt(alpha))
         atten_all = tfd["color_obj_atten_all"].to(self.device, torch.float32).expand_as(grad_lat).contiguous()
         return ops.latent_guidance_update(latents.contiguous(), grad_lat.contiguous(), atten_all,
                                           float(tfd["color_guidance_weight"]))
@@ -260,7 +274,8 @@ class RegionDiffusionXL:
         st.ones = torch.ones(1, latents[0].numel(), dtype=torch.float32, device=dev)
         st.passes = self.build_pass_batch(N, inject)
         st.kind = {p["kind"] + str(p.get("region", "")): k for k, p in enumerate(st.passes)}
-        st.plan = region_parallel.RegionParallelPlan(st.passes, inject, group=self.region_group)
+        st.plan = region_parallel.RegionParallelPlan(st.passes, inject, group=self.region_group,
+                                                     remote_qk=self.remote_qk and self.fused_exchange)
         word_pos, font_size = tfd.get("word_pos"), tfd.get("font_size")
         if word_pos is not None and font_size is not None:
             if int(word_pos.max()) >= ctx.shape[1] or int(word_pos.min()) < 0:   # the reference's advanced indexing raises here
@@ -283,30 +298,42 @@ class RegionDiffusionXL:
         key = (tuple(local), inj)
         kvc = st.kv_caches.setdefault(tuple(local), CrossKVCache())
 
+        rq = self._remote_qk(st, x) if inj else None
+        role = plan.remote_role(local) if rq is not None else None
+
         def make_ctrl():
             ctrl = RegionControl(kv_cache=kvc)
             if inj:
                 src = plan.injection_sources(local)                                     # :1018-1061
-                ctrl.qk_src = src
-                ctrl.feature_src = src
-                ikey = ("idx",) + key
-                if ikey not in st.graphs:   # built once, outside any capture
-                    st.graphs[ikey] = torch.as_tensor(src, device=self.device)
-                ctrl.feature_idx = st.graphs[ikey]
+                if src is not None:         # None: this rank's region passes take pass D's tensors from another rank
+                    ctrl.qk_src = src
+                    ctrl.feature_src = src
+                    ikey = ("idx",) + key
+                    if ikey not in st.graphs:   # built once, outside any capture
+                        st.graphs[ikey] = torch.as_tensor(src, device=self.device)
+                    ctrl.feature_idx = st.graphs[ikey]
+                if rq is not None:
+                    ctrl.remote = rq.begin_pass(role)
             if st.word_pos is not None:
                 ctrl.word_pos, ctrl.font_size = st.word_pos, st.font_size               # :792-797
                 ctrl.fs_batch_mask = sum(1 << k for k, p in enumerate(local) if passes[p]["kind"] == "B")
             return ctrl
 
+        def unet(*a):
+            out = self.unet(*a)["sample"]
+            if rq is not None:
+                rq.end_pass()
+            return out
+
         if not self.use_cuda_graphs:
-            return self.unet(x, t, st.ctx[rows], {"text_embeds": st.pooled[rows], "time_ids": st.time_ids}, make_ctrl())["sample"]
+            return unet(x, t, st.ctx[rows], {"text_embeds": st.pooled[rows], "time_ids": st.time_ids}, make_ctrl())
         g = st.graphs.get(key)
         if g is None:
             g = {"x": torch.empty_like(x), "t": torch.zeros(1, dtype=torch.float32, device=self.device),
                  "ctx": st.ctx[rows].contiguous(), "added": {"text_embeds": st.pooled[rows].contiguous(), "time_ids": st.time_ids}}
             g["x"].copy_(x)
             g["t"].fill_(float(t))
-            run = lambda: self.unet(g["x"], g["t"], g["ctx"], g["added"], make_ctrl())["sample"]
+            run = lambda: unet(g["x"], g["t"], g["ctx"], g["added"], make_ctrl())
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):      # warm-up outside capture: fills the prompt K/V cache, sets func attributes
@@ -327,6 +354,24 @@ class RegionDiffusionXL:
         ops._count(g["launches"])
         return g["out"]
 
+    def _remote_qk(self, st, x):
+        """RemoteQK buffers for this latent shape (created collectively by every rank of the region group on the first
+        feature-injection step), or None: single GPU, remote_qk off, no peer-mappable memory, or the plan replicates D."""
+        if not (st.plan.remote_qk and st.plan.world > 1):
+            return None
+        key = (int(x.shape[2]), int(x.shape[3]))
+        if key not in self._remote:
+            try:
+                self._remote[key] = region_parallel.RemoteQK(self.unet.injection_layout(*key), self.device, group=self.region_group)
+            except Exception as e:   # no peer-mappable memory (the same on every rank): replicate pass D instead
+                import warnings
+                warnings.warn(f"rtti_b200: RemoteQK unavailable ({e!r}); pass D is replicated on the region-pass ranks")
+                self._remote[key] = None
+        if self._remote[key] is None:
+            st.plan.remote_qk = False
+            st.plan._cache.clear()
+        return self._remote[key]
+
     def rich_text_step(self, st, i):
         """One iteration of the region loop, models/region_diffusion_sdxl.py:779-878."""
         t = st.timesteps[i]
@@ -335,6 +380,8 @@ class RegionDiffusionXL:
         background_inject_step = i < st.inject_background * st.n_t                      # :783
         sigma = self.scheduler.sigma(t)
         scale = 1.0 / math.sqrt(sigma * sigma + 1.0)                                    # :784
+        if feat_inject_step and st.inject:
+            self._remote_qk(st, st.latents)   # collective on first use: every rank of the group, also those without passes
         local = plan.local_passes(feat_inject_step)
         pe = self.profile_events
         if pe is not None:

@@ -42,9 +42,16 @@ class _Pad:
 class StripeArena:
     """Symmetric arena: [4 KB control block][pad half 0][pad half 1], identical layout on every rank.
 
-    Control block: +0 GroupNorm {sequence, error} words; +64 halo flags {from_up, from_down, error, counter};
-    +256 GroupNorm sum slots fp32 [2 parities][2 * 32 groups]. Pads alternate between the two halves by exchange
-    sequence parity (see csrc/stripe_exchange.cu for why two are enough)."""
+    Control block: +0 GroupNorm {sequence, error, ..., [8] sequence base} words; +64 halo flags {from_up, from_down,
+    error, counter, ..., [8] sequence base}; +256 GroupNorm sum slots fp32 [2 parities][2 * 32 groups]. Pads alternate
+    between the two halves by exchange sequence parity (see csrc/stripe_exchange.cu for why two are enough).
+
+    Sequence numbers are RELATIVE to one decoder evaluation (forward + backward): the host counts 1..n, the kernels add
+    the device-side base words, and end_call() advances the bases by n with a stream-ordered kernel. Every evaluation
+    therefore issues identical kernel arguments and can be replayed from one CUDA graph. Restarting the pad-half
+    alternation at each evaluation is safe because an evaluation ends with collectives over all ranks (all-gather of the
+    conv_in gradient, broadcast of the latent gradient) that order every rank's last pad consumer before any rank's
+    next push."""
     HEADER = 4096
 
     def __init__(self, pad_bytes, device, group=None):
@@ -103,6 +110,14 @@ class StripeArena:
                           self.halo_flags[self.rank],
                           self.halo_flags[up] if up is not None else 0,
                           self.halo_flags[down] if down is not None else 0, seq)
+
+    def end_call(self):
+        """End of one decoder evaluation: advance the device-side sequence bases by the exchanges issued and restart
+        the relative numbering."""
+        if self.halo_seq or self.gn_seq:
+            ops.peer_seq_advance(self.halo_flags[self.rank], self.halo_seq, self.base[self.rank], self.gn_seq)
+        self.halo_seq = 0
+        self.gn_seq = 0
 
     def check(self):
         """Raise if a peer wait timed out (error words set by the kernels)."""
@@ -335,6 +350,9 @@ class StripedDecoderFwdBwd(DecoderFwdBwd):
             self.tape = None
             out = g.view(1, H, W, -1).permute(0, 3, 1, 2).contiguous()
             dist.broadcast(out, src=dist.get_global_rank(self.group, 0), group=self.group)
+            end_call = getattr(self.arena, "end_call", None)   # emulated arenas (tests) count absolutely
+            if end_call is not None:
+                end_call()
             return out
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev

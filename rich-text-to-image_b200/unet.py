@@ -140,6 +140,9 @@ class RegionControl:
     capture: Optional[TokenMapAccumulator] = None
     capture_row: int = 1                        # batch row kept by the capture (the conditional one)
     kv_cache: Optional[CrossKVCache] = None
+    # multi-GPU, injection steps: hand-off of pass D's self-attention Q|K and resnet feature between ranks
+    # (region_parallel.RemoteQK role object: .is_src / .is_dst, push / wait / views), None = everything is local
+    remote: Optional[object] = None
 
 
 def _f16(t):
@@ -232,15 +235,33 @@ class BasicTransformerBlock(nn.Module):
         B, T, C = h.shape
         heads = self.attn1.heads
         # ---- self-attention (attention.py:150-160)
-        qkv = F.linear(n, self.attn1.fused_weight())
-        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         cap = ctrl.capture
-        tgt = cap.self_target(name + ".attn1", T, h.device) if cap is not None else None
-        lse = torch.empty(B, heads, T, dtype=torch.float32, device=h.device) if tgt is not None else None
-        o = ops.attention(q, k, v, heads, qk_src=ctrl.qk_src, lse=lse)
-        if tgt is not None:
-            r = ctrl.capture_row
-            ops.attn_probs_mean_accum(q[r], k[r], lse[r], tgt[0], heads)
+        rem = ctrl.remote
+        if rem is not None and rem.is_dst:
+            # region passes whose score source (pass D) runs on another rank: Q and K arrive in this layer's receive
+            # buffer; the entries' own Q, K would be discarded (attention_processor.py:1160-1163), so only V is projected
+            k0 = rem.n_own                                   # leading entries that compute their own scores
+            w3 = self.attn1.fused_weight()
+            o = torch.empty(B, T, C, dtype=h.dtype, device=h.device)
+            if k0:
+                qkv = F.linear(n[:k0], w3)
+                ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, out=o[:k0])
+            v = F.linear(n[k0:], w3[2 * C:])
+            rqk = rem.wait(T, 2 * C)                         # [1, T, 2C] of pass D, stream-ordered behind the wait
+            ops.attention(rqk[..., :C], rqk[..., C:], v, heads, qk_src=[0] * (B - k0), out=o[k0:])
+        else:
+            qkv = F.linear(n, self.attn1.fused_weight())
+            q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+            if rem is not None and rem.is_src:
+                rem.push(qkv[rem.d_index, :, :2 * C])        # side stream: overlaps this rank's own attention kernel
+            tgt = cap.self_target(name + ".attn1", T, h.device) if cap is not None else None
+            lse = torch.empty(B, heads, T, dtype=torch.float32, device=h.device) if tgt is not None else None
+            o = ops.attention(q, k, v, heads, qk_src=ctrl.qk_src, lse=lse)
+            if rem is not None and rem.is_src:
+                rem.join()                                   # qkv may be recycled from here on
+            if tgt is not None:
+                r = ctrl.capture_row
+                ops.attn_probs_mean_accum(q[r], k[r], lse[r], tgt[0], heads)
         a = F.linear(o, self.attn1.to_out[0].weight)
         h, n = ops.add_bias_layernorm(a, h, self.attn1.to_out[0].bias, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         # ---- cross-attention (attention.py:163-178)
@@ -318,15 +339,22 @@ class ResnetBlock2D(nn.Module):
         self.conv2 = Conv2dCL(cout, cout, 3, padding=1)
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
-    def forward(self, x, H, W, temb_act, feature_idx=None):
-        """x [B, HW, Cin]; temb_act = silu(temb). Returns output [B, HW, Cout] (resnet.py:591-645)."""
+    def forward(self, x, H, W, temb_act, feature_idx=None, remote=None):
+        """x [B, HW, Cin]; temb_act = silu(temb). Returns output [B, HW, Cout] (resnet.py:591-645).
+        `remote` (multi-GPU): the injected feature of pass D is pushed to / received from another rank."""
         h = self.norm1(x, silu=True)
         h, _, _ = self.conv1.forward_cl(h, H, W, with_bias=False)
         # conv1 bias + `hidden_states + temb` (resnet.py:621-622) both folded into norm2 as a per-(batch, channel) bias
         t = F.linear(temb_act, self.time_emb_proj.weight, self.time_emb_proj.bias + self.conv1.bias)
         h = self.norm2(h, silu=True, chan_bias=t.contiguous())
         h, _, _ = self.conv2.forward_cl(h, H, W, with_bias=False)
-        if feature_idx is not None:
+        if remote is not None and remote.is_src:
+            remote.push(h[remote.d_index])
+            remote.join()
+        if remote is not None and remote.is_dst:
+            f = remote.wait(h.shape[1], h.shape[2])          # conv2 output of pass D, [1, HW, C]
+            h = torch.cat([h[:remote.n_own], f.expand(h.shape[0] - remote.n_own, -1, -1)], 0)
+        elif feature_idx is not None:
             # inject_states of the reference pass replaces the residual branch (resnet.py:639-641)
             h = h.index_select(0, feature_idx)
         if self.conv_shortcut is not None:
@@ -418,6 +446,33 @@ class UNet2DConditionModel(nn.Module):
         self.conv_norm_out = GroupNormCL(g, boc[0], eps)
         self.conv_out = Conv2dCL(boc[0], cfg.out_channels, 3, padding=1)
 
+    def injection_layout(self, H, W):
+        """(tokens, width) of every activation the region passes take from pass D on a feature-injection step, in
+        execution order: the Q|K slab [tokens, 2C] of each self-attention layer and the conv2 output [tokens, C] of
+        FEATURE_INJECT_RESNET (models/region_diffusion_sdxl.py:1018-1061). Mirrors the traversal of forward()."""
+        out = []
+
+        def attn(tr, H, W):
+            C = tr.proj_in.weight.shape[0]
+            out.extend([(H * W, 2 * C)] * len(tr.transformer_blocks))
+
+        for i, blk in enumerate(self.down_blocks):
+            for l in range(len(blk.resnets)):
+                if blk.has_cross_attention:
+                    attn(blk.attentions[l], H, W)
+            if blk.downsamplers is not None:
+                H, W = (H + 1) // 2, (W + 1) // 2
+        attn(self.mid_block.attentions[0], H, W)
+        for i, blk in enumerate(self.up_blocks):
+            for l, res in enumerate(blk.resnets):
+                if f"up_blocks.{i}.resnets.{l}" == FEATURE_INJECT_RESNET:
+                    out.append((H * W, res.conv2.weight.shape[0]))
+                if blk.has_cross_attention:
+                    attn(blk.attentions[l], H, W)
+            if blk.upsamplers is not None:
+                H, W = 2 * H, 2 * W
+        return out
+
     # ------------------------------------------------------------------ weights
     def finalize(self, device="cuda"):
         """fp16, on device, 3x3 conv weights in channels_last so cuDNN picks NHWC tensor-core kernels."""
@@ -500,7 +555,8 @@ class UNet2DConditionModel(nn.Module):
                 s, _, _ = skips.pop()
                 h = torch.cat([h, s], dim=-1)
                 rname = f"up_blocks.{i}.resnets.{l}"
-                h = res(h, H, W, temb_act, feat_idx if rname == FEATURE_INJECT_RESNET else None)
+                inj = rname == FEATURE_INJECT_RESNET
+                h = res(h, H, W, temb_act, feat_idx if inj else None, ctrl.remote if inj else None)
                 if blk.has_cross_attention:
                     h = blk.attentions[l](h, ctx, ctrl, f"up_blocks.{i}.attentions.{l}")
             if blk.upsamplers is not None:

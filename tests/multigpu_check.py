@@ -59,7 +59,37 @@ def check_stripe_guidance(rank, world):
                 print(f"stripe guidance [{name}] world={world} rep={rep}: image rel err {e_img:.2e}, latent-grad rel err {e_g:.2e}, "
                       f"ranks bit-identical: {same}, striped {e0.elapsed_time(e1):.2f} ms vs replicated {e1.elapsed_time(e2):.2f} ms "
                       f"({'OK' if good else 'FAIL'})", flush=True)
-        del eng, ref_eng, vae
+        # the same evaluation as ONE replayed CUDA graph (vae_guidance.GuidanceGraph: call 1 eager, call 2 captures, then
+        # replays; the exchange sequence numbers come from the device-side base words)
+        from rtti_b200 import ops
+        from rtti_b200.vae_guidance import GuidanceGraph
+        gg = GuidanceGraph(eng)
+        masks = torch.rand(1, hw * 8, hw * 8, generator=gen).cuda()
+        tgt = torch.tensor([[0.9, 0.4, 0.6]], device="cuda")
+        for rep in range(4):
+            z = torch.randn(1, 4, hw, hw, generator=gen).cuda()
+            img_r = ref_eng.forward(z)
+            loss_r, gi = ops.color_loss_fwd_bwd(img_r[0].contiguous(), masks, tgt)
+            g_r = ref_eng.backward(gi[None])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss_s, g_s = gg(z, masks, tgt)
+            e1.record()
+            torch.cuda.synchronize()
+            eng.arena.check()
+            e_g = float((g_s - g_r).abs().max() / g_r.abs().max())
+            e_l = abs(float(loss_s) - float(loss_r)) / abs(float(loss_r))
+            gathered = [torch.empty_like(g_s) for _ in range(world)]
+            dist.all_gather(gathered, g_s.contiguous())
+            same = all(torch.equal(gathered[0], x) for x in gathered)
+            good = e_g < 5e-3 and e_l < 2e-3 and same and bool(torch.isfinite(g_s).all())
+            ok &= good
+            if rank == 0:
+                mode = "eager" if rep == 0 else ("capture+replay" if rep == 1 else "replay")
+                print(f"graphed guidance [{name}] world={world} call {rep} ({mode}): latent-grad rel err {e_g:.2e}, loss rel err {e_l:.2e}, "
+                      f"ranks bit-identical: {same}, {e0.elapsed_time(e1):.2f} ms ({'OK' if good else 'FAIL'})", flush=True)
+        del gg, eng, ref_eng, vae
         torch.cuda.empty_cache()
     return ok
 
@@ -84,9 +114,9 @@ def main():
     tfd.update(synth.color_dict(inp["masks"], S, 1.0))
     ok = True
     results = {}
-    for fused in (True, False):
+    for fused, remote in ((True, True), (True, False), (False, False)):
         model = RegionDiffusionXL(device="cuda", unet=unet, vae=synth.TinyVAE("cuda"))
-        model.fused_exchange = fused
+        model.fused_exchange, model.remote_qk = fused, remote
         model.masks = [m.cuda() for m in inp["masks"]]
         out = model.sample(height=S * 8, width=S * 8, num_inference_steps=4, guidance_scale=8.5, latents=inp["latents"].clone(),
                            prompt_embeds=ctx[1:], negative_prompt_embeds=ctx[:1], pooled_prompt_embeds=te[1:],
@@ -101,9 +131,14 @@ def main():
         dist.all_gather(gathered, out.contiguous())
         same = all(torch.equal(gathered[0], x) for x in gathered)
         results[fused] = out
+        for rq in model._remote.values():
+            if rq is not None and rq.error():
+                good = False
+                print(f"rank {rank}: RemoteQK wait timed out", flush=True)
         ok &= good and same
         if rank == 0:
-            print(f"world={world} fused_exchange={fused}: max err vs reference golden {err.max().item():.4f} "
+            print(f"world={world} fused_exchange={fused} remote_qk={remote} (pass D {'on one rank, Q|K pushed' if remote else 'replicated'}): "
+                  f"max err vs reference golden {err.max().item():.4f} "
                   f"({'OK' if good else 'FAIL'}), ranks bit-identical: {same}", flush=True)
     # fewer passes than ranks on the non-injection steps (world >= 4): some ranks only take part in the exchange
     inp2 = synth.synth_inputs(cfg.cross_attention_dim, pooled, 2, S, 32)

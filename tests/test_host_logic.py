@@ -25,6 +25,32 @@ def test_library_exports_every_declared_symbol():
     assert lib.rtti_color_loss_workspace_elems(2, 1024 * 1024) > 0
 
 
+def test_tensor_core_kernels_fit_the_launch_time_register_check():
+    """The hardware verifies a launch's register demand with the CTA's warp count rounded up to the 4 SM sub-partitions
+    (cuda_occupancy.h, "Hardware check"): a 9-warp CTA is checked as 12 warps. A kernel over the limit compiles and
+    links but every launch fails with cudaErrorLaunchOutOfResources — found only on the GPU (round 2: attn_cross at
+    9 warps x 210 registers). Checked here from the cubin resource usage, no GPU needed."""
+    import shutil
+    import subprocess
+    from rtti_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    _lib.load()
+    out = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    threads = {"attn_cross_kernel": 288, "attn_self_kernelILi6E": 288, "attn_self_kernelILi1E": 160, "attn_fwd_kernel": 192,
+               "attn_probs_mean": 192, "ff_geglu_kernel": 320}
+    seen = set()
+    for fn, regs in re.findall(r"Function (\S+):\s*\n\s*REG:(\d+)", out):
+        for key, nthreads in threads.items():
+            if key in fn:
+                seen.add(key)
+                warps = (nthreads + 31) // 32
+                per_warp = (int(regs) * 32 + 255) // 256 * 256
+                assumed = per_warp * ((warps + 3) // 4 * 4)
+                assert assumed <= 65536, f"{fn}: {regs} registers x {warps} warps is checked as {assumed} > 65536 registers"
+    assert seen == set(threads), f"kernels not found in the library: {set(threads) - seen}"
+
+
 def test_ops_fail_loudly_without_gpu_or_library():
     from rtti_b200 import _lib, ops
     x = torch.zeros(1, 16, 64, dtype=torch.float16)
@@ -60,6 +86,52 @@ def test_pass_assignment_plans():
                     assert max(len(a) for a in assign) == -(-len(kinds) // world)
     assign, _ = assign_passes(list("ABCDEEEE"), 2, True)
     assert max(len(a) for a in assign) == 5
+
+
+def test_remote_qk_assignment_roles_and_layout():
+    """remote_qk: pass D runs on one rank and its Q|K / feature travel to the region-pass ranks, so the passes of an
+    injection step are spread evenly (round 1 replicated D: 2 passes on the busiest of 8 ranks for the 8-pass step)."""
+    from rtti_b200.region_parallel import RegionParallelPlan, assign_passes
+    from rtti_b200.unet import UNet2DConditionModel, UNetConfig
+    for n_regions in (3, 5, 8, 10):
+        kinds = ["A", "B", "C", "D"] + ["E"] * (n_regions - 1)
+        for world in (2, 4, 8):
+            assign, owner = assign_passes(kinds, world, True, remote_qk=True)
+            assert sorted(p for a in assign for p in a) == list(range(len(kinds))), "every pass exactly once"
+            assert max(len(a) for a in assign) == -(-len(kinds) // world)
+            assert all(a == sorted(a) for a in assign)
+            roles = []
+            for r in range(world):
+                plan = RegionParallelPlan([dict(kind=k) for k in kinds], True, remote_qk=True)
+                plan.world, plan.rank = world, r                       # no process group in this test
+                local = plan.local_passes(True)
+                role = plan.remote_role(local)
+                roles.append(role)
+                src = plan.injection_sources(local)
+                has_d = kinds.index("D") in local
+                has_e = any(kinds[p] == "E" for p in local)
+                if has_e and not has_d:
+                    assert role[0] == "dst" and src is None
+                    assert [kinds[p] for p in local[role[1]:]] == ["E"] * (len(local) - role[1])
+                elif has_d:
+                    assert src is not None and all(src[k] == local.index(kinds.index("D")) for k, p in enumerate(local) if kinds[p] == "E")
+            srcs = [r for r in roles if r is not None and r[0] == "src"]
+            dsts = [i for i, r in enumerate(roles) if r is not None and r[0] == "dst"]
+            if dsts:
+                assert len(srcs) == 1 and srcs[0][2] == dsts
+            else:
+                assert not srcs
+    # the 8-pass SDXL step on 8 ranks: one pass per rank
+    assign, owner = assign_passes(list("ABCDEEEE"), 8, True, remote_qk=True)
+    assert [len(a) for a in assign] == [1] * 8
+    # layout: SDXL has 70 self-attention layers (10 at 64^2 with C=640, 60 at 32^2 with C=1280) + the injected feature
+    with torch.device("meta"):
+        unet = UNet2DConditionModel(UNetConfig.sdxl())
+    lay = unet.injection_layout(128, 128)
+    assert len(lay) == 71
+    assert sorted(set(lay)) == [(1024, 2560), (4096, 640), (4096, 1280)]
+    assert lay.count((4096, 1280)) == 10 and lay.count((1024, 2560)) == 60 and lay.count((4096, 640)) == 1
+    assert sum(r * w * 2 for r, w in lay) == 10 * 4096 * 1280 * 2 + 60 * 1024 * 2560 * 2 + 4096 * 640 * 2
 
 
 def test_injection_sources():
