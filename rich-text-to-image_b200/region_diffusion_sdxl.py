@@ -301,7 +301,7 @@ class RegionDiffusionXL:
         rq = self._remote_qk(st, x) if inj else None
         role = plan.remote_role(local) if rq is not None else None
 
-        def make_ctrl():
+        def make_ctrl(remote=True):
             ctrl = RegionControl(kv_cache=kvc)
             if inj:
                 src = plan.injection_sources(local)                                     # :1018-1061
@@ -312,37 +312,40 @@ class RegionDiffusionXL:
                     if ikey not in st.graphs:   # built once, outside any capture
                         st.graphs[ikey] = torch.as_tensor(src, device=self.device)
                     ctrl.feature_idx = st.graphs[ikey]
-                if rq is not None:
+                if rq is not None and remote:
                     ctrl.remote = rq.begin_pass(role)
             if st.word_pos is not None:
                 ctrl.word_pos, ctrl.font_size = st.word_pos, st.font_size               # :792-797
                 ctrl.fs_batch_mask = sum(1 << k for k, p in enumerate(local) if passes[p]["kind"] == "B")
             return ctrl
 
-        def unet(*a):
-            out = self.unet(*a)["sample"]
-            if rq is not None:
+        def unet(x_, t_, ctx_, added_, remote=True):
+            """`remote=False`: the eager warm-up before a capture — pass D's tensors are neither pushed nor awaited
+            (region passes use their own Q, K; the result is discarded). Producer and consumers then execute the
+            hand-off exactly once per step — in the replayed graph — which is what keeps the single-buffered receive
+            regions safe and every rank's sequence base in step."""
+            out = self.unet(x_, t_, ctx_, added_, make_ctrl(remote))["sample"]
+            if rq is not None and remote:
                 rq.end_pass()
             return out
 
         if not self.use_cuda_graphs:
-            return unet(x, t, st.ctx[rows], {"text_embeds": st.pooled[rows], "time_ids": st.time_ids}, make_ctrl())
+            return unet(x, t, st.ctx[rows], {"text_embeds": st.pooled[rows], "time_ids": st.time_ids})
         g = st.graphs.get(key)
         if g is None:
             g = {"x": torch.empty_like(x), "t": torch.zeros(1, dtype=torch.float32, device=self.device),
                  "ctx": st.ctx[rows].contiguous(), "added": {"text_embeds": st.pooled[rows].contiguous(), "time_ids": st.time_ids}}
             g["x"].copy_(x)
             g["t"].fill_(float(t))
-            run = lambda: unet(g["x"], g["t"], g["ctx"], g["added"], make_ctrl())
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):      # warm-up outside capture: fills the prompt K/V cache, sets func attributes
-                run()
+                unet(g["x"], g["t"], g["ctx"], g["added"], remote=False)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES
             with torch.cuda.graph(graph, pool=st.graphs.get("pool")):
-                g["out"] = run()
+                g["out"] = unet(g["x"], g["t"], g["ctx"], g["added"])
             g["launches"] = ops.LAUNCHES - n0   # rtti kernels inside the graph (for the launch accounting)
             if "pool" not in st.graphs:   # the graphs of one sampling call share a memory pool
                 st.graphs["pool"] = graph.pool()
@@ -392,6 +395,10 @@ class RegionDiffusionXL:
             eps_local = self._unet_pass(st, x, t, local, feat_inject_step)
         else:   # more ranks than passes on this step: this rank only takes part in the exchange
             eps_local = st.latents.new_empty((0,) + tuple(st.latents.shape[1:]))
+            rq = self._remote_qk(st, st.latents) if (feat_inject_step and st.inject) else None
+            if rq is not None:   # keep this rank's sequence base in step with the ranks that ran a pass
+                rq.begin_pass(None)
+                rq.end_pass()
         if pe is not None:
             ev[1].record()
         dt = self.scheduler.dt(t)

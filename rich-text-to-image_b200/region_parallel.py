@@ -301,12 +301,13 @@ class RemoteQK:
         return v
 
     def end_pass(self):
-        """All events of the pass issued: advance the sequence base by their number (src and dst ranks alike)."""
+        """End of an injection-step pass: advance the sequence base by the number of events — on EVERY rank of the
+        group, whatever its role (a rank without a role today may be a consumer in the next sampling call, and producer
+        and consumers compare absolute numbers: their bases must move together)."""
         from . import ops
-        if self.role is not None:
-            if self.event != len(self.layout):
-                raise RuntimeError(f"RemoteQK: the pass issued {self.event} of {len(self.layout)} events")
-            ops.peer_seq_advance(self.base[self.rank], self.event)
+        if self.role is not None and self.event != len(self.layout):
+            raise RuntimeError(f"RemoteQK: the pass issued {self.event} of {len(self.layout)} events")
+        ops.peer_seq_advance(self.base[self.rank], len(self.layout))
         self.role = None
 
     def error(self):
