@@ -477,7 +477,11 @@ extern "C" int rtti_attn_fwd(const void* q, const void* k, const void* v, void* 
   dim3 grid((n_q + 127) / 128, (heads + p.heads_per_cta - 1) / p.heads_per_cta, batch);
   cudaStream_t st = (cudaStream_t)stream;
 #define RTTI_LAUNCH(KT_, ND_, CAP_) return launch<KT_, ND_, CAP_>(tq, tk, tv, to, p, grid, st)
-  if (KT == 80 && ndch == 1 && !want_cap)   // persistent streaming kernel (attn_cross.cu); capture / head_dim > 64 stay here
+  bool own_scores = true;   // every entry computes its own probabilities (no injection)
+  for (int i = 0; i < batch; ++i) own_scores = own_scores && p.qk_src[i] == i;
+  // persistent streaming kernel (attn_cross.cu) for the plain / font-size case; capture, head_dim > 64, a requested
+  // log-sum-exp or injected probabilities (self-attention over <= 80 tokens, e.g. an 8x8 mid block) stay in this file
+  if (KT == 80 && ndch == 1 && !want_cap && lse == nullptr && own_scores)
     return launch_attn_cross(tq, tk, tv, to, batch, heads, head_dim, n_q, n_k, p.scale_log2, p.fs_mask, word_pos, font_size,
                              p.n_fs, st);
   if (KT == 80) {

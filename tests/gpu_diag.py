@@ -220,6 +220,13 @@ CASES = {
     "d160_cross": lambda: attn_case(2, 8, 160, 64, 77, fs=True),
     "d32": lambda: attn_case(2, 2, 32, 64, 64),
     "d8": lambda: attn_case(2, 4, 8, 64, 77),
+    # self-attention over <= 80 tokens (an 8x8 mid block) takes the one-key-tile path: with a requested log-sum-exp /
+    # token-map capture recompute, and with injected probabilities (regression: round 2 routed both to the streaming
+    # cross kernel, which has neither)
+    "self_64tok_lse_pm": lambda: attn_case(2, 8, 32, 64, 64, want_lse=True),
+    "self_64tok_inject": lambda: attn_case(4, 8, 32, 64, 64, qk_src=[0, 1, 1, 1]),
+    # Q / K handed over from another tensor (pass D's slab in a RemoteQK receive buffer): q, k batch 1, v batch 3
+    "self_remote_qk": lambda: remote_qk_case(),
     "cross_xl64": lambda: attn_case(8, 10, 64, 4096, 77),
     "self_xl32": lambda: attn_case(8, 20, 64, 1024, 1024, fused_qkv=True),
     # grouped PV (attn_self.cu): entries sharing a score source are served by one softmax
@@ -235,6 +242,25 @@ CASES = {
     # grouping disabled (RTTI_ATTN_MAX_GROUP=1): every entry evaluates its own softmax from its source's Q, K
     "g1:self_group5": lambda: attn_case(8, 2, 64, 512, 512, qk_src=[0, 1, 2, 3, 3, 3, 3, 3], fused_qkv=True),
 }
+
+
+def remote_qk_case():
+    """ops.attention with q / k of batch 1 (another pass's Q|K slab, strided like a [1, T, 2C] receive buffer) and v of
+    batch 3: every entry applies softmax(q k^T) of entry 0 to its own values — plain (1 entry) and grouped (3 entries)."""
+    import torch
+    from rtti_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    H, D, T = 4, 64, 384
+    C = H * D
+    qk = torch.randn(1, T, 2 * C, device="cuda", generator=g).half()
+    ok = True
+    for B in (1, 3):
+        v = torch.randn(B, T, C, device="cuda", generator=g).half()
+        o = ops.attention(qk[..., :C], qk[..., C:], v, H, qk_src=[0] * B)
+        torch.cuda.synchronize()
+        o_ref, _, _ = ref_attention(qk[..., :C].expand(B, -1, -1).contiguous(), qk[..., C:].expand(B, -1, -1).contiguous(), v, H)
+        ok &= report(f"remote qk B{B}", o, o_ref, 2e-3, 2e-2)
+    return ok
 
 
 def rescale_case():
