@@ -253,12 +253,10 @@ class BasicTransformerBlock(nn.Module):
             qkv = F.linear(n, self.attn1.fused_weight())
             q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
             if rem is not None and rem.is_src:
-                rem.push(qkv[rem.d_index, :, :2 * C])        # side stream: overlaps this rank's own attention kernel
+                rem.push(qkv[rem.d_index, :, :2 * C])        # side stream: overlaps the rest of this block (joined at its end)
             tgt = cap.self_target(name + ".attn1", T, h.device) if cap is not None else None
             lse = torch.empty(B, heads, T, dtype=torch.float32, device=h.device) if tgt is not None else None
             o = ops.attention(q, k, v, heads, qk_src=ctrl.qk_src, lse=lse)
-            if rem is not None and rem.is_src:
-                rem.join()                                   # qkv may be recycled from here on
             if tgt is not None:
                 r = ctrl.capture_row
                 ops.attn_probs_mean_accum(q[r], k[r], lse[r], tgt[0], heads)
@@ -291,7 +289,14 @@ class BasicTransformerBlock(nn.Module):
             g = ops.ff_geglu(n, proj.weight, proj.bias)     # GEMM + bias + gate in one kernel; no [B, T, 8C] intermediate
         else:
             g = ops.geglu(F.linear(n, proj.weight, proj.bias))
-        return h, F.linear(g, self.ff.net[2].weight), self.ff.net[2].bias
+        a = F.linear(g, self.ff.net[2].weight)
+        if rem is not None and rem.is_src:
+            # the push of this layer's Q|K has had the whole block to drain (at batch 1 it outlasts the attention kernel
+            # it was forked next to: 21 MB to four consumers vs ~25 us); `qkv` is still referenced, so its memory was not
+            # recycled by the allocator in between
+            rem.join()
+            del qkv
+        return h, a, self.ff.net[2].bias
 
 
 class Transformer2DModel(nn.Module):
