@@ -529,7 +529,7 @@ def run_product_xl(args, rank, world, local_rank):
         if c:
             gbs = c[2] / c[0] / 1e9
             ctraffic, cnote = ncu_traffic("attn_fwd_kernel_cross")
-            cross = {"kernel": "attn_fwd_kernel<80,1> (cross-attention, 77 keys)", "bound": "hbm", "achieved": gbs,
+            cross = {"kernel": "attn_cross_kernel (cross-attention, 77 keys, font-size re-weighting on pass B; persistent, TMA ring + tcgen05/TMEM)", "bound": "hbm", "achieved": gbs,
                      "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "tensor_tflops": c[1] / c[0] / 1e12,
                      "traffic": ctraffic, "traffic_note": cnote,
                      "launches_timed": c[3], "ms_per_step_in_kernel": c[0] * 1e3 / n_prof}
