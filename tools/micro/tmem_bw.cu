@@ -33,10 +33,10 @@ __global__ void __launch_bounds__(128) tmem_kernel(int iters, unsigned long long
 #pragma unroll
         for (int i = 0; i < 64; ++i) acc += ex2_approx(__uint_as_float(r[i]) * 1e-9f);
       } else {
-        acc += __uint_as_float(r[it & 63]);
+        acc += __uint_as_float(r[0] ^ r[63]);   // static indices only: a dynamic index would move r[] to local memory
       }
     } else {
-      r[it & 63] += 1;
+      r[0] += 1;
       tmem_st32(t, r); tmem_st32(t + 32, r + 32); tmem_wait_st();
     }
   }
