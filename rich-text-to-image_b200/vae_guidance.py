@@ -106,7 +106,8 @@ class DecoderFwdBwd:
         k = F.linear(hn, a.to_k.weight, a.to_k.bias)
         v = F.linear(hn, a.to_v.weight, a.to_v.bias)
         scale = 1.0 / math.sqrt(C)
-        p = torch.softmax(torch.bmm(q, k.transpose(1, 2)) * scale, dim=-1)
+        # the softmax scale is applied to q ([T, C], 33 MB) instead of the [T, T] scores (1 GB at 1024^2: a 2 GB pass)
+        p = torch.softmax(torch.bmm(q * scale, k.transpose(1, 2)), dim=-1)
         o = torch.bmm(p, v)
         tape.append(("attn", a, hn, q, k, v, p, scale))
         return x + F.linear(o, a.to_out[0].weight, a.to_out[0].bias)
@@ -116,9 +117,9 @@ class DecoderFwdBwd:
         do = g @ a.to_out[0].weight                       # [B,T,C]
         dv = torch.bmm(p.transpose(1, 2), do)
         dp = torch.bmm(do, v.transpose(1, 2))
-        ds = torch._softmax_backward_data(dp, p, -1, p.dtype) * scale
-        dq = torch.bmm(ds, k)
-        dk = torch.bmm(ds.transpose(1, 2), q)
+        ds = torch._softmax_backward_data(dp, p, -1, p.dtype)   # d/d(scaled scores); the scale goes onto the small operands
+        dq = torch.bmm(ds, k * scale)
+        dk = torch.bmm(ds.transpose(1, 2), q * scale)
         dhn = dq @ a.to_q.weight + dk @ a.to_k.weight + dv @ a.to_v.weight
         return g + self._gn_b(tape.pop(), dhn)
 
