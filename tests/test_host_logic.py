@@ -167,6 +167,49 @@ def test_schedulers_match_oracle_restatement():
     np.testing.assert_allclose(xa.numpy(), xb.numpy(), atol=1e-5)
 
 
+def test_schedulers_known_answers_and_analytic_properties():
+    """The scheduler arithmetic is third-party (diffusers 0.18.2, not in the reference tree). Checks that do NOT rest on
+    the repo's own restatement: (i) the published constants of the Stable Diffusion noise schedule (scaled-linear betas
+    0.00085..0.012, 1000 steps: sigma_min 0.0292, sigma_max 14.6146 as quoted by k-diffusion / the SD model cards);
+    (ii) Euler discrete integrates dx/dsigma = eps exactly for a constant eps: x_final = x_0 - eps * sigma_0 for any
+    number of steps (telescoping); (iii) PLMS / DDIM transfer: with a constant eps the sample stays on the ray
+    x_t = sqrt(a_t) x0 + sqrt(1 - a_t) eps, so after ALL steps it must equal sqrt(a_f) x0 + sqrt(1 - a_f) eps with
+    a_f the cumulative alpha reached by the last step (the multistep combinations 3/2,-1/2 ... have coefficient sum 1)."""
+    from rtti_b200.schedulers import EulerDiscreteScheduler, PNDMScheduler
+    e = EulerDiscreteScheduler()
+    ac = e.alphas_cumprod.double()
+    sig = ((1 - ac) / ac).sqrt()
+    assert abs(float(sig[-1]) - 14.6146) < 2e-3 and abs(float(sig[0]) - 0.0292) < 1e-4
+    assert abs(float(ac[0]) - 0.99915) < 1e-6 and abs(float(ac[-1]) - 0.004660) < 2e-5
+    g = torch.Generator().manual_seed(1)
+    x0, eps = torch.randn(1, 4, 8, 8, generator=g), torch.randn(1, 4, 8, 8, generator=g)
+    for n in (7, 41, 50):
+        e.set_timesteps(n)
+        assert float(e.timesteps[0]) == (n - 1) * (1000 // n) + 1 and float(e.timesteps[-1]) == 1.0   # `leading`, offset 1
+        s0 = e.sigma(e.timesteps[0])
+        x = x0 * e.init_noise_sigma
+        for t in e.timesteps:
+            x = e.step(eps, t, x)["prev_sample"]
+        np.testing.assert_allclose(x.numpy(), (x0 * e.init_noise_sigma - eps * s0).numpy(), atol=2e-5)
+        assert abs(e.init_noise_sigma - (s0 * s0 + 1) ** 0.5) < 1e-6
+        xs = e.scale_model_input(x0, e.timesteps[0])
+        np.testing.assert_allclose(xs.numpy(), (x0 / (s0 * s0 + 1) ** 0.5).numpy(), atol=1e-6)
+    p = PNDMScheduler()
+    acp = p.alphas_cumprod.double()
+    for n in (10, 41):
+        p.set_timesteps(n)
+        ts = p.timesteps.tolist()
+        assert len(ts) == n + 1 and ts[0] == (n - 1) * (1000 // n) + 1 and ts[-1] == 1
+        a0 = float(acp[ts[0]])
+        x = (a0 ** 0.5) * x0 + ((1 - a0) ** 0.5) * eps
+        for t in p.timesteps:
+            x = p.step(eps, t, x)["prev_sample"]
+        prev = ts[-1] - 1000 // n                      # the last transfer goes to t = 1 - ratio < 0 -> final_alpha_cumprod
+        af = float(acp[prev]) if prev >= 0 else float(acp[0])
+        want = (af ** 0.5) * x0 + ((1 - af) ** 0.5) * eps
+        np.testing.assert_allclose(x.numpy(), want.numpy(), atol=5e-5)
+
+
 def test_token_map_accumulator_call_counting():
     from rtti_b200.unet import TokenMapAccumulator
     acc = TokenMapAccumulator(["c"], self_layers=["s"], start_after=2, sd_overwrite_bug=True, self_resolutions=None)
