@@ -51,6 +51,31 @@ def test_tensor_core_kernels_fit_the_launch_time_register_check():
     assert seen == set(threads), f"kernels not found in the library: {set(threads) - seen}"
 
 
+def test_fp16_hbm_kernels_use_128_bit_global_accesses():
+    """Round 2 found (ncu + SASS) that `*reinterpret_cast<const Half8*>(p)` had been lowered to FOUR 32-bit LDG/STG in
+    every fp16 elementwise kernel. Checked from the cubin: the streaming kernels must move their tensors with
+    LDG.E.128 / STG.E.128 and contain no plain 32-bit global store."""
+    import shutil
+    import subprocess
+    from rtti_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    _lib.load()
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)[1:]
+    want = ("layernorm_kernelILi5", "add_bias_layernorm_kernelILi5", "add_bias_layernorm_kernelILi3", "add_bias_f16_kernel",
+            "4rtti12geglu_kernel", "gn_apply_kernel")
+    seen = set()
+    for f in funcs:
+        name = f.split("\n", 1)[0]
+        for w in want:
+            if w in name:
+                seen.add(w)
+                assert re.search(r"\bLDG\.E\.128", f) and re.search(r"\bSTG\.E\.128", f), f"{name}: no 128-bit global accesses"
+                assert not re.search(r"\bSTG\.E\s", f), f"{name}: 32-bit global stores"
+    assert seen == set(want), f"kernels not found: {set(want) - seen}"
+
+
 def test_ops_fail_loudly_without_gpu_or_library():
     from rtti_b200 import _lib, ops
     x = torch.zeros(1, 16, 64, dtype=torch.float16)
