@@ -121,3 +121,41 @@ def test_richtext_utils_match_the_reference_functions(ref, delta):
     assert same(cr, cp) and set(tr2) == set(tp2)
     for k in tr2:
         assert same(tr2[k], tp2[k]), k
+
+
+@pytest.mark.parametrize("n_prompts,steps,inject_selfattn,inject_background,use_guidance,with_fs,seed", [
+    (4, 3, 0.4, 0.0, False, True, 71),      # more regions, self-attention / feature injection on the first step only
+    (2, 3, 0.0, 0.4, True, False, 72),      # configs[3]-like: background injection only (the joint-stepping quirk), colour guidance
+])
+def test_xl_rich_loop_live_reference_other_settings(ref, n_prompts, steps, inject_selfattn, inject_background, use_guidance,
+                                                    with_fs, seed):
+    """RegionDiffusionXL.sample(run_rich_text=True) of the UNMODIFIED reference (models/region_diffusion_sdxl.py:772-878)
+    against the oracle's rich_text_loop at settings the committed fixtures do not cover: other region counts, step
+    counts, injection windows, with / without font sizes and colour guidance."""
+    from oracle import gen_golden as gg, sampler_oracle as sam, schedulers_oracle as so
+    from tests import synth
+    if ref.region_diffusion_sdxl is None:
+        pytest.skip(ref.region_diffusion_sdxl_error)
+    cfg = uo.tiny_xl_config()
+    S = 128   # the reference asserts a 64-wide injected feature map (sdxl.py:1090): 1024^2 images only
+    inp = gg.synth_inputs(cfg, n_prompts, S, seed)
+    ctx, te = inp["ctx"], inp["text_embeds"]
+    m = gg.make_xl_sampler(ref, cfg, 5, (ctx[1:], ctx[:1], te[1:], te[:1]))
+    m.masks = inp["masks"]
+    tfd = gg.text_format(1, S, seed, with_fs=with_fs)
+    if use_guidance:
+        tfd.update(gg.color_dict(inp["masks"], S, weight=0.7))
+    out = m.sample(["p"] * n_prompts, height=S * 8, width=S * 8, num_inference_steps=steps, guidance_scale=6.0,
+                   negative_prompt=[""], latents=inp["latents"].clone(), output_type="latent", use_guidance=use_guidance,
+                   inject_selfattn=inject_selfattn, inject_background=inject_background, text_format_dict=dict(tfd),
+                   run_rich_text=True).images.detach()
+    sd = uo.make_state_dict(cfg, 5)
+    sch = so.EulerDiscreteSchedulerOracle()
+    sch.set_timesteps(steps)
+    added = {"text_embeds": te, "time_ids": inp["time_ids"]}
+    lat = sam.rich_text_loop(sam.make_unet_fn(sd, cfg), sch, ctx, inp["masks"], inp["latents"].clone() * sch.init_noise_sigma,
+                             steps, 6.0, xl=True, added_cond=added, use_guidance=use_guidance, text_format_dict=dict(tfd),
+                             inject_selfattn=inject_selfattn, inject_background=inject_background,
+                             vae_decode=synth.TinyVAE() if use_guidance else None, scaling_factor=0.13025)
+    assert torch.isfinite(out).all()
+    torch.testing.assert_close(lat, out, atol=5e-4, rtol=1e-4)
