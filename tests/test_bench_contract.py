@@ -75,3 +75,36 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_committed_bench_lines_carry_every_contract_key():
+    """The JSON lines measured on the B200 boxes this round (profiles/r02_bench_*.json) against the keys the driver's
+    contract lists: metric / value / unit / n_gpus / steps / warmup / ms_per_step / higher_is_better / scaling /
+    vs_baseline / dtype / data / config.workload / clocks / gpu_launches / e2e{value, unit, h2d, d2h}; config 3 at N = 1
+    also roofline{bound, achieved, peak, unit, frac, traffic}; N > 1 lines the rank-identity flag."""
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench_n*_config*.json")))
+    assert len(paths) >= 8
+    for p in paths:
+        line = [l for l in open(p) if l.startswith("{")][-1]
+        d = json.loads(line)
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches", "e2e"):
+            assert k in d, (p, k)
+        assert d["metric"] == "denoising steps/sec" and d["unit"] == "steps/s" and d["higher_is_better"] is True
+        assert d["scaling"] == "strong" and d["vs_baseline"] is None and d["data"] == "synthetic" and d["warmup"] >= 3
+        assert "workload" in d["config"] and "model" not in d["config"]
+        assert abs(d["value"] - d["steps"] / (d["ms_per_step"] * d["steps"] * 1e-3)) < 1e-6 * d["value"]
+        assert d["gpu_launches"] > 0
+        e = d["e2e"]
+        assert e["value"] > 0 and e["unit"] == "steps/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if d["config"]["config_id"] == 3:
+            r = d["roofline"]
+            assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+            assert r["traffic"] and (0.3 < r["frac"] < 0.7 if d["n_gpus"] == 1 else 0.05 < r["frac"] < 0.7)   # batch-1 passes at N = 8
+            assert d["roofline_cross_attention"]["bound"] == "hbm"
+        if d["n_gpus"] > 1:
+            assert d["ranks_bit_identical"] is True
+            if d.get("single_gpu_check"):
+                assert d["single_gpu_check"]["pass"] is True
